@@ -1,0 +1,275 @@
+"""Synthetic CFD meshes and the static per-mesh attributes the hot path reads.
+
+The reference builds these attributes with its transforms (datasets/transforms stay
+in the reference; they are OUT of the replaced path).  The benchmark and the tests
+still need 10k ... 4M-node inputs in exactly the reference's layouts, and the
+reference versions are O(E^2) Python loops (transforms/remus.py:36,159-161) or need
+torch_cluster, so the layouts are rebuilt here in vectorised numpy:
+
+* ``knn_edges``          = transforms/connect.py:9-71  (non-periodic branch): edges
+                           (neighbour -> centre), grouped by centre, k per centre
+* ``grid_clustering``    = transforms/mus.py:9-37
+* ``guillard_coarsening``= transforms/mugs.py:8-29
+* ``extend_graph``       = transforms/remus.py:9-44    (closed form of angle_index)
+* ``angle_index_down``   = transforms/remus.py:151-176
+* ``knn_interp_weights`` = transforms/interpolate.py:110-129
+
+``tests/test_mesh_layouts.py`` checks every one of them against the reference's own
+transform on the same points (in the build container, where the reference exists).
+"""
+import math
+from typing import Sequence
+
+import numpy as np
+import torch
+
+
+class Mesh:
+    """Attribute bag with the slice of ``torch_geometric.data.Data`` that
+    ``GNN.solve`` (nn/model.py:303-321) touches: ``num_nodes``, ``to`` and plain attributes."""
+
+    def __init__(self, **kwargs):
+        for key, val in kwargs.items():
+            setattr(self, key, val)
+
+    @property
+    def num_nodes(self):
+        return self.pos.size(0)
+
+    @property
+    def num_edges(self):
+        return self.edge_index.size(1)
+
+    def to(self, device, *args, **kwargs):
+        for key, val in list(self.__dict__.items()):
+            if torch.is_tensor(val):
+                setattr(self, key, val.to(device))
+        return self
+
+    def clone(self):
+        out = Mesh()
+        for key, val in self.__dict__.items():
+            out.__dict__[key] = val.clone() if torch.is_tensor(val) else val
+        return out
+
+    def keys(self):
+        return list(self.__dict__)
+
+
+# --------------------------------------------------------------------------- points
+def jittered_points(n: int, seed: int = 0, box=(4.0, 1.0), jitter: float = 0.35) -> torch.Tensor:
+    """n points on a jittered lattice in [0,box_x]x[0,box_y], numbered column by column
+    (x-major strips), so a contiguous node range is a vertical strip of the domain."""
+    rng = np.random.default_rng(seed)
+    ny = max(1, int(round(math.sqrt(n * box[1] / box[0]))))
+    nx = (n + ny - 1) // ny
+    h = box[1] / ny
+    ix, iy = np.divmod(np.arange(n, dtype=np.int64), ny)
+    pos = np.stack([(ix + 0.5) * (box[0] / nx), (iy + 0.5) * h], axis=1)
+    pos += rng.uniform(-jitter, jitter, size=pos.shape) * np.array([box[0] / nx, h])
+    return torch.from_numpy(pos.astype(np.float32))
+
+
+def uniform_points(n: int, seed: int = 0, box=(1.0, 1.0)) -> torch.Tensor:
+    rng = np.random.default_rng(seed)
+    return torch.from_numpy((rng.uniform(0, 1, size=(n, 2)) * np.array(box)).astype(np.float32))
+
+
+# ----------------------------------------------------------------------------- kNN
+def knn_edges(pos: torch.Tensor, k: int):
+    """(edge_index int64[2, N*k], edge_attr fp32[N*k, 2]); edge j*k+m points from the
+    m-th nearest neighbour of node j to node j (all in-edges of a node are contiguous)."""
+    from scipy.spatial import cKDTree
+    pts = pos.double().numpy()
+    n = pts.shape[0]
+    _, nbr = cKDTree(pts).query(pts, k=k + 1, workers=-1)
+    nbr = nbr.astype(np.int64)
+    self_col = nbr == np.arange(n)[:, None]
+    # drop the node itself (normally column 0; with duplicated points fall back to the last hit)
+    none = ~self_col.any(axis=1)
+    self_col[none, k] = True
+    nbr = nbr[~self_col].reshape(n, k)
+    centre = np.repeat(np.arange(n, dtype=np.int64), k)
+    edge_index = torch.from_numpy(np.stack([nbr.reshape(-1), centre]))
+    edge_attr = pos[edge_index[1]] - pos[edge_index[0]]
+    return edge_index, edge_attr
+
+
+def knn_interp_weights(pos_x: torch.Tensor, pos_y: torch.Tensor, k: int):
+    """for every y its k nearest x: (y_idx, x_idx, 1/max(d^2,1e-16))."""
+    from scipy.spatial import cKDTree
+    _, nbr = cKDTree(pos_x.double().numpy()).query(pos_y.double().numpy(), k=k, workers=-1)
+    nbr = np.asarray(nbr, dtype=np.int64).reshape(pos_y.size(0), k)
+    y_idx = torch.from_numpy(np.repeat(np.arange(pos_y.size(0), dtype=np.int64), k))
+    x_idx = torch.from_numpy(nbr.reshape(-1))
+    diff = pos_x[x_idx] - pos_y[y_idx]
+    weights = 1.0 / torch.clamp((diff * diff).sum(dim=-1, keepdim=True), min=1e-16)
+    return y_idx, x_idx, weights
+
+
+# ------------------------------------------------------------------ MuS (grid) levels
+def grid_clustering(pos_1: torch.Tensor, cell_size: float):
+    """(pos_2, cluster_2, mask_2, idx1_to_idx2, e_12) with the reference's numbering:
+    coarse nodes are the non-empty cells in ascending cell id (x fastest)."""
+    p = pos_1
+    start = p.min(dim=0).values
+    end = p.max(dim=0).values
+    size = torch.tensor([cell_size, cell_size], dtype=p.dtype)
+    num_voxels = ((end - start) / size).to(torch.long) + 1
+    coord = ((p - start) / size).to(torch.long)
+    cluster = coord[:, 0] + coord[:, 1] * num_voxels[0]
+    mask, inverse = torch.unique(cluster, sorted=True, return_inverse=True)
+    n2 = mask.numel()
+    summed = torch.zeros(n2, 2, dtype=p.dtype).index_add_(0, inverse, p)
+    count = torch.zeros(n2, dtype=p.dtype).index_add_(0, inverse, torch.ones(p.size(0), dtype=p.dtype))
+    pos_2 = summed / count.clamp(min=1).unsqueeze(1)
+    e_12 = (pos_2[inverse] - p) / cell_size
+    return pos_2, cluster, mask, inverse, e_12
+
+
+# -------------------------------------------------------------- REMuS (Guillard) levels
+def guillard_coarsening(edge_index: torch.Tensor, num_nodes: int) -> torch.Tensor:
+    """Sequential node-nested coarsening: visiting nodes in order, a node still marked
+    coarse removes its k senders from the coarse set."""
+    k = int((edge_index[1] == 0).sum())
+    senders = edge_index[0].view(-1, k).numpy()
+    try:
+        from . import _lib
+        return torch.from_numpy(_lib.host_guillard(senders, int(num_nodes)))
+    except Exception:
+        pass
+    coarse = np.ones(int(num_nodes), dtype=bool)
+    for i in range(senders.shape[0]):
+        if coarse[i]:
+            coarse[senders[i]] = False
+    return torch.from_numpy(coarse)
+
+
+def _local_index(edge_index: torch.Tensor):
+    """Level-l edge_index is stored in LEVEL-1 node numbering (transforms/remus.py:120-122);
+    map it back to 0..V_l-1 through the sorted target ids (targets are grouped ascending)."""
+    k = int((edge_index[1] == edge_index[1][0]).sum())
+    owners = edge_index[1].view(-1, k)[:, 0].contiguous()
+    local = torch.searchsorted(owners, edge_index.reshape(-1)).view(2, -1)
+    return local, owners, k
+
+
+def extend_graph(edge_index: torch.Tensor, edge_attr: torch.Tensor, k: int):
+    """(edgeUnitVector[E,2], angle_index[2,kE], angle_attr[kE,4]).  Angle j*k+m goes from
+    the m-th in-edge of the SOURCE node of edge j into edge j: row = src_local(j)*k+m, col = j."""
+    num_edges = edge_index.size(1)
+    local, _, _ = _local_index(edge_index)
+    size = edge_attr.norm(2, dim=1, keepdim=True)
+    unit = edge_attr / size
+    row = (local[0].unsqueeze(1) * k + torch.arange(k)).reshape(-1)
+    col = torch.arange(num_edges).repeat_interleave(k)
+    cos = (unit[row] * unit[col]).sum(dim=1)
+    sin = unit[row, 0] * unit[col, 1] - unit[row, 1] * unit[col, 0]
+    angle_attr = torch.cat([size[row], size[col], cos.unsqueeze(1), sin.unsqueeze(1)], dim=1)
+    return unit, torch.stack([row, col]), angle_attr
+
+
+def angle_index_down(edge_index1, edge_attr1, edge_index2, edge_attr2, coarse_index2, k):
+    """Inter-level angles: for every coarse node j (ascending) and every level-2 edge (j->q)
+    leaving it (ascending edge id), the k level-1 in-edges of j are the senders."""
+    local1, owners1, _ = _local_index(edge_index1)
+    # position of each coarse node among the level-1 targets -> its k in-edges
+    pos_in_l1 = torch.searchsorted(owners1, coarse_index2)
+    in_edges = pos_in_l1.unsqueeze(1) * k + torch.arange(k)                      # [V2, k]
+    # level-2 edges grouped by source node, ascending node then ascending edge id
+    src2 = torch.searchsorted(coarse_index2, edge_index2[0])
+    order = torch.sort(src2, stable=True).indices                                # out_edges_index2
+    row = in_edges[src2[order]].reshape(-1)
+    col = order.repeat_interleave(k)
+    size1 = edge_attr1.norm(2, dim=1, keepdim=True)
+    size2 = edge_attr2.norm(2, dim=1, keepdim=True)
+    u1, u2 = edge_attr1 / size1, edge_attr2 / size2
+    cos = (u1[row] * u2[col]).sum(dim=1)
+    sin = u1[row, 0] * u2[col, 1] - u1[row, 1] * u2[col, 0]
+    attr = torch.cat([size1[row], size2[col], cos.unsqueeze(1), sin.unsqueeze(1)], dim=1)
+    return torch.stack([row, col]), attr
+
+
+# ------------------------------------------------------------------- synthetic fields
+def _fields(pos: torch.Tensor, num_fields: int, n_in: int = 1):
+    x, y = pos[:, 0], pos[:, 1]
+    base = [0.5 + 0.3 * torch.sin(3 * x) * torch.cos(5 * y),
+            0.2 * torch.cos(2 * x) * torch.sin(4 * y),
+            -0.1 + 0.4 * torch.sin(x + 2 * y)]
+    cols = []
+    for t in range(n_in):
+        for f in range(num_fields):
+            cols.append(base[f % 3] * (1.0 - 0.02 * t))
+    return torch.stack(cols, dim=1).contiguous()
+
+
+def _omega(pos: torch.Tensor):
+    x, y = pos[:, 0], pos[:, 1]
+    box_x = float(x.max())
+    om = ((x < 0.01 * box_x) | (((x - 0.25 * box_x) ** 2 + (y - 0.5) ** 2) < 0.01)).float()
+    return om.unsqueeze(1)
+
+
+def build_mus_mesh(n: int, k: int = 6, cells: Sequence[float] = (), seed: int = 0,
+                   points: str = "jittered", num_fields: int = 3, edge_scale=None,
+                   glob: float = 0.3) -> Mesh:
+    """MuS-GNN input: level-1 kNN graph + ``len(cells)`` grid-clustered levels.
+    ``cells`` in units of the mean edge length when given as ("auto", ratio...) is not
+    supported; pass absolute sizes (see ``auto_cells``)."""
+    pos = jittered_points(n, seed) if points == "jittered" else uniform_points(n, seed)
+    edge_index, edge_attr = knn_edges(pos, k)
+    r = float(edge_attr.norm(dim=1).mean()) if edge_scale is None else edge_scale
+    edge_attr = edge_attr / (2 * r)
+    m = Mesh(pos=pos, edge_index=edge_index, edge_attr=edge_attr,
+             field=_fields(pos, num_fields), glob=torch.full((n, 1), glob), omega=_omega(pos))
+    p = pos
+    for lvl, cell in enumerate(cells, start=2):
+        pos_l, cluster, mask, idx, e = grid_clustering(p, cell)
+        setattr(m, f'pos_{lvl}', pos_l)
+        setattr(m, f'cluster_{lvl}', cluster)
+        setattr(m, f'mask_{lvl}', mask)
+        setattr(m, f'idx{lvl - 1}_to_idx{lvl}', idx)
+        setattr(m, f'e_{lvl - 1}{lvl}', e)
+        p = pos_l
+    return m
+
+
+def auto_cells(n: int, levels: int, box=(4.0, 1.0), ratios=(5.0, 20.0, 80.0)):
+    """cell sizes giving N_2 ~ N/5, N_3 ~ N/20, N_4 ~ N/80 (the reference example's ratios)."""
+    area = box[0] * box[1]
+    return [math.sqrt(area * ratios[i] / n) for i in range(levels - 1)]
+
+
+def build_remus_mesh(n: int, k: int = 6, seed: int = 0, points: str = "jittered",
+                     interp_k: int = None, edge_scale=(None, None, None)) -> Mesh:
+    """REMuS-GNN 3-level input in the layouts of transforms/remus.py:93-147 +
+    transforms/interpolate.py:147-155."""
+    interp_k = k if interp_k is None else interp_k
+    pos = jittered_points(n, seed) if points == "jittered" else uniform_points(n, seed)
+    m = Mesh(pos=pos, field=_fields(pos, 2), glob=torch.full((n, 1), 0.3), omega=_omega(pos))
+
+    def scaled(ei, ea, s):
+        r = float(ea.norm(dim=1).mean()) if s is None else s
+        return ei, ea / (2 * r)
+
+    m.edge_index, m.edge_attr = scaled(*knn_edges(pos, k), edge_scale[0])
+    m.coarse_mask2 = guillard_coarsening(m.edge_index, n)
+    ci2 = m.coarse_mask2.nonzero().squeeze(1)
+    ei2, m.edge_attr2 = scaled(*knn_edges(pos[ci2], k), edge_scale[1])
+    m.coarse_mask3 = torch.zeros_like(m.coarse_mask2)
+    m.coarse_mask3[m.coarse_mask2] = guillard_coarsening(ei2, ci2.numel())
+    ci3 = m.coarse_mask3.nonzero().squeeze(1)
+    ei3, m.edge_attr3 = scaled(*knn_edges(pos[ci3], k), edge_scale[2])
+    m.edge_index2, m.edge_index3 = ci2[ei2], ci3[ei3]
+    for sfx, ei, ea, nl in (("", m.edge_index, m.edge_attr, n), ("2", m.edge_index2, m.edge_attr2, ci2.numel()),
+                            ("3", m.edge_index3, m.edge_attr3, ci3.numel())):
+        unit, ai, aa = extend_graph(ei, ea, k)
+        setattr(m, "edgeUnitVector" + sfx, unit)
+        setattr(m, "angle_index" + sfx, ai)
+        setattr(m, "angle_attr" + sfx, aa)
+        setattr(m, "edgeUnitVectorInverse" + sfx, torch.linalg.pinv(unit.view(nl, k, 2)))
+    m.angle_index12, m.angle_attr12 = angle_index_down(m.edge_index, m.edge_attr, m.edge_index2, m.edge_attr2, ci2, k)
+    m.angle_index23, m.angle_attr23 = angle_index_down(m.edge_index2, m.edge_attr2, m.edge_index3, m.edge_attr3, ci3, k)
+    m.y_idx_21, m.x_idx_21, m.weights_21 = knn_interp_weights(pos[m.coarse_mask2], pos, interp_k)
+    m.y_idx_32, m.x_idx_32, m.weights_32 = knn_interp_weights(pos[m.coarse_mask3], pos[m.coarse_mask2], interp_k)
+    return m

@@ -1,0 +1,64 @@
+"""The oracle restatement (oracle/restate.py) held to vectors produced by the UNMODIFIED
+reference (tests/golden/*.pt, written by oracle/make_golden.py)."""
+import pytest
+import torch
+
+from conftest import load_golden, mesh_from, rel_l2
+from oracle import restate as R
+
+TOL = 1e-6   # same ATen ops in the same order: expected bit-exact, tolerance for BLAS blocking only
+
+
+@pytest.mark.parametrize("name", ["mp_trained_h128", "mp_irregular_mean_h32", "mp_irregular_sum_h32", "mp_h64"])
+def test_gn_block(name):
+    d = load_golden(name)
+    v, e = R.gn_block(d["params"], "mp", d["v"], d["e"], d["edge_index"], d["aggr"])
+    assert rel_l2(v, d["v_out"]) <= TOL and rel_l2(e, d["e_out"]) <= TOL
+
+
+@pytest.mark.parametrize("name", ["mlp_enc", "mlp_ln2", "mlp_dec", "mlp_dec1"])
+def test_mlp(name):
+    d = load_golden(name)
+    assert rel_l2(R.mlp(d["params"], "m", d["x"]), d["y"]) <= TOL
+
+
+def test_down_up():
+    d = load_golden("down_up_h32")
+    g = mesh_from(d["mesh"])
+    f_l, ei_l, ea_l = R.down_mp(d["params"], "down", g.field, g.e_12, g.idx1_to_idx2, g.edge_index, g.edge_attr)
+    assert torch.equal(ei_l, d["edge_index_l"])
+    assert rel_l2(f_l, d["field_l"]) <= TOL and rel_l2(ea_l, d["edge_attr_l"]) <= TOL
+    f_h = R.up_mp(d["params"], "up", f_l, g.field, g.e_12, g.idx1_to_idx2)
+    assert rel_l2(f_h, d["field_h_up"]) <= TOL
+
+
+def test_remus_blocks():
+    d = load_golden("remus_blocks_h32")
+    g, p = mesh_from(d["mesh"]), d["params"]
+    e1o, a1o = R.edge_mp(p, "emp", d["e1"], d["a1"], g.angle_index)
+    assert rel_l2(e1o, d["e1_out"]) <= TOL and rel_l2(a1o, d["a1_out"]) <= TOL
+    assert rel_l2(R.down_edge_mp(p, "dmp", d["e1"], d["e2"], d["a12"], g.angle_index12), d["e2_down"]) <= TOL
+    n = g.pos.size(0)
+    e1u = R.up_edge_mp(p, "ump", n, g.y_idx_21, g.x_idx_21, g.weights_21, d["e2"], g.edgeUnitVectorInverse2,
+                       d["e1"], g.edge_index[1], g.edgeUnitVector)
+    assert rel_l2(e1u, d["e1_up"]) <= TOL
+    e2u = R.up_edge_mp(p, "ump", n, g.y_idx_32, g.x_idx_32, g.weights_32, d["e3"], g.edgeUnitVectorInverse3,
+                       d["e2"], g.edge_index2[1], g.edgeUnitVector2, g.coarse_mask2)
+    assert rel_l2(e2u, d["e2_up"]) <= TOL
+    assert rel_l2(R.edge_scalar_to_node_vector(d["e1"], g.edgeUnitVectorInverse), d["node_vec"]) <= TOL
+
+
+@pytest.mark.parametrize("name", ["model_ns1_h16", "model_ns2_h16", "model_ns3_h32", "model_ns4_h16",
+                                  "model_adv3_h16", "model_remus_h32"])
+def test_model_rollout(name):
+    d = load_golden(name)
+    out = R.solve(d["params"], mesh_from(d["mesh"]), d["n_out"])
+    assert out.shape == d["out"].shape
+    assert rel_l2(out, d["out"]) <= TOL
+
+
+def test_program_derivation():
+    d = load_golden("model_ns3_h32")
+    kinds = [k for _, k in R.block_program(d["params"])]
+    assert kinds == ["mlp", "mlp"] + ["mp"] * 4 + ["down"] + ["mp"] * 2 + ["down"] + ["mp"] * 4 + ["up"] + ["mp"] * 2 \
+        + ["up"] + ["mp"] * 4 + ["mlp"]

@@ -1,0 +1,66 @@
+"""Live pin (build container only): restatement and mesh-layout builders against the
+reference's own classes / transforms imported verbatim from /root/reference."""
+import pytest
+import torch
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.reference
+
+
+@pytest.fixture(scope="module")
+def gfd():
+    from oracle.pyg_stub import import_reference
+    return import_reference()
+
+
+def test_shipped_3s_checkpoint_one_step(gfd):
+    from graphs4cfd_b200 import mesh as M
+    from oracle import restate as R
+    model = gfd.nn.NsThreeScaleGNN(model="3S-GNN-NsCircle-v1")
+    n = 2000
+    g = M.build_mus_mesh(n, 6, M.auto_cells(n, 3), seed=3)
+    ref = model.solve(g.clone(), 2)
+    out = R.solve({k: v.detach() for k, v in model.state_dict().items()}, g.clone(), 2)
+    assert rel_l2(out, ref) <= 1e-6
+
+
+def test_shipped_remus_checkpoint_one_step(gfd):
+    from graphs4cfd_b200 import mesh as M
+    from oracle import restate as R
+    model = gfd.nn.NsRotEquiTreeScaleGNN(model="RE3S-GNN-NsEllipse-v1")
+    g = M.build_remus_mesh(400, 5, seed=5, points="uniform")
+    ref = model.solve(g.clone(), 2)
+    out = R.solve({k: v.detach() for k, v in model.state_dict().items()}, g.clone(), 2)
+    assert rel_l2(out, ref) <= 1e-6
+
+
+def test_mus_layouts_match_reference_transforms(gfd):
+    from graphs4cfd_b200 import mesh as M
+    n = 1500
+    cells = M.auto_cells(n, 4)
+    g = M.build_mus_mesh(n, 6, cells, seed=2)
+    ei, ea = gfd.transforms.connect_knn(g.pos, 6)
+    assert torch.equal(ei, g.edge_index)
+    ref = gfd.transforms.GridClustering(cells)(M.Mesh(pos=g.pos.clone()))
+    for lvl in (2, 3, 4):
+        for name in (f"pos_{lvl}", f"cluster_{lvl}", f"mask_{lvl}", f"idx{lvl-1}_to_idx{lvl}", f"e_{lvl-1}{lvl}"):
+            a, b = getattr(g, name), getattr(ref, name)
+            assert torch.equal(a, b) if not a.is_floating_point() else torch.allclose(a, b, atol=1e-6), name
+
+
+def test_remus_layouts_match_reference_transforms(gfd):
+    from graphs4cfd_b200 import mesh as M
+    k = 5
+    g = M.build_remus_mesh(300, k, seed=9, points="uniform", edge_scale=(0.1, 0.2, 0.4))
+    ref = M.Mesh(pos=g.pos.clone(), field=g.field.clone())
+    ref = gfd.transforms.BuildRemusGraph(num_levels=3, k=k, scale_edge_length=(0.1, 0.2, 0.4))(ref)
+    ref = gfd.transforms.BuildKnnInterpWeights(k)(ref)
+    for name in ("edge_index", "edge_index2", "edge_index3", "coarse_mask2", "coarse_mask3", "angle_index",
+                 "angle_index2", "angle_index3", "angle_index12", "angle_index23", "y_idx_21", "x_idx_21",
+                 "y_idx_32", "x_idx_32"):
+        assert torch.equal(getattr(g, name), getattr(ref, name)), name
+    for name in ("edge_attr", "edge_attr2", "edge_attr3", "edgeUnitVector", "edgeUnitVector2", "edgeUnitVector3",
+                 "edgeUnitVectorInverse", "edgeUnitVectorInverse2", "edgeUnitVectorInverse3", "angle_attr",
+                 "angle_attr2", "angle_attr3", "angle_attr12", "angle_attr23", "weights_21", "weights_32"):
+        assert rel_l2(getattr(g, name), getattr(ref, name)) <= 1e-5, name
