@@ -1,0 +1,146 @@
+"""ctypes binding of libg4c.so (include/g4c.h).  There is NO fallback: if the shared library is
+missing or a call fails, a RuntimeError is raised — the product path never silently runs on
+PyTorch eager or on the CPU oracle."""
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libg4c.so")
+
+ACT_NONE, ACT_SELU, ACT_TANH = 0, 1, 2
+AGGR_MEAN, AGGR_SUM = 0, 1
+PREC_FP32, PREC_FP16X3, PREC_BF16 = 0, 1, 2
+PRECISIONS = {"fp32": PREC_FP32, "fp16x3": PREC_FP16X3, "bf16": PREC_BF16}
+ACTS = {None: ACT_NONE, "none": ACT_NONE, "selu": ACT_SELU, "tanh": ACT_TANH}
+MAX_LAYERS, MAX_SEGS = 3, 3
+
+_f32p = C.c_void_p
+_i32p = C.c_void_p
+
+
+class Mlp(C.Structure):
+    _fields_ = [("n_layers", C.c_int32), ("in_width", C.c_int32), ("hidden", C.c_int32), ("out_width", C.c_int32),
+                ("W_t", _f32p * MAX_LAYERS), ("b", _f32p * MAX_LAYERS), ("ln_gamma", _f32p), ("ln_beta", _f32p)]
+
+
+class Seg(C.Structure):
+    _fields_ = [("ptr", _f32p), ("gather", _i32p), ("width", C.c_int32), ("stride", C.c_int32),
+                ("scale", C.c_float), ("_pad", C.c_int32)]
+
+
+class RowMlpDesc(C.Structure):
+    _fields_ = [("rows", C.c_int64), ("n_segs", C.c_int32), ("act_out", C.c_int32), ("seg", Seg * MAX_SEGS),
+                ("mlp", Mlp), ("out", _f32p), ("out_stride", C.c_int32), ("res_stride", C.c_int32),
+                ("residual", _f32p)]
+
+
+class MpDesc(C.Structure):
+    _fields_ = [("hidden", C.c_int32), ("aggr", C.c_int32), ("fixed_k", C.c_int32), ("act_e_out", C.c_int32),
+                ("act_t_out", C.c_int32), ("precision", C.c_int32), ("n_targets", C.c_int64), ("n_edges", C.c_int64),
+                ("rowptr", _i32p), ("src", _i32p), ("edge_perm", _i32p), ("tgt_perm", _i32p),
+                ("e_in", _f32p), ("src_feat", _f32p), ("tgt_feat", _f32p), ("e_out", _f32p), ("t_out", _f32p),
+                ("edge_mlp", Mlp), ("node_mlp", Mlp)]
+
+
+class SegReduceDesc(C.Structure):
+    _fields_ = [("n_groups", C.c_int64), ("width", C.c_int32), ("aggr", C.c_int32), ("act_out", C.c_int32),
+                ("_pad", C.c_int32), ("ptr", _i32p), ("idx", _i32p), ("x", _f32p), ("out", _f32p)]
+
+
+class ProjectDesc(C.Structure):
+    _fields_ = [("n_edges", C.c_int64), ("n_feat", C.c_int32), ("n_extra", C.c_int32), ("col", _i32p),
+                ("V", _f32p), ("U", _f32p), ("extra", _f32p * 2), ("out", _f32p)]
+
+
+class EdgeToNodeDesc(C.Structure):
+    _fields_ = [("n_nodes", C.c_int64), ("k", C.c_int32), ("n_feat", C.c_int32), ("Uinv", _f32p), ("e", _f32p),
+                ("V", _f32p), ("out_stride", C.c_int32), ("res_stride", C.c_int32), ("residual", _f32p)]
+
+
+class InterpDesc(C.Structure):
+    _fields_ = [("n_out", C.c_int64), ("k", C.c_int32), ("width", C.c_int32), ("x_idx", _i32p), ("w", _f32p),
+                ("y_row", _i32p), ("x", _f32p), ("y", _f32p)]
+
+
+class StepUpdateDesc(C.Structure):
+    _fields_ = [("n_nodes", C.c_int64), ("nf", C.c_int32), ("field_width", C.c_int32), ("in_stride", C.c_int32),
+                ("out_stride", C.c_int32), ("t", C.c_int32), ("_pad", C.c_int32), ("pred", _f32p),
+                ("node_in", _f32p), ("outputs", _f32p)]
+
+
+class HaloDesc(C.Structure):
+    _fields_ = [("n_rows", C.c_int64), ("width", C.c_int32), ("_pad", C.c_int32), ("idx", _i32p),
+                ("src", _f32p), ("dst", _f32p)]
+
+
+EXPORTS = {
+    "g4c_version": (C.c_int, []),
+    "g4c_last_error": (C.c_char_p, []),
+    "g4c_launch_count": (C.c_int64, []),
+    "g4c_rowmlp_fwd": (C.c_int, [C.POINTER(RowMlpDesc), C.c_void_p]),
+    "g4c_mp_fwd": (C.c_int, [C.POINTER(MpDesc), C.c_void_p]),
+    "g4c_seg_reduce_fwd": (C.c_int, [C.POINTER(SegReduceDesc), C.c_void_p]),
+    "g4c_project_fwd": (C.c_int, [C.POINTER(ProjectDesc), C.c_void_p]),
+    "g4c_edge_to_node_fwd": (C.c_int, [C.POINTER(EdgeToNodeDesc), C.c_void_p]),
+    "g4c_interp_fwd": (C.c_int, [C.POINTER(InterpDesc), C.c_void_p]),
+    "g4c_step_update": (C.c_int, [C.POINTER(StepUpdateDesc), C.c_void_p]),
+    "g4c_halo_pack": (C.c_int, [C.POINTER(HaloDesc), C.c_void_p]),
+    "g4c_halo_unpack": (C.c_int, [C.POINTER(HaloDesc), C.c_void_p]),
+    "g4c_host_guillard": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load libg4c.so once; raise loudly if it has not been built (python __graft_entry__.py build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: build it with `make -C graphs4cfd_b200/csrc` "
+                               "(or `python -c 'import __graft_entry__ as g; g.build()'`). "
+                               "graphs4cfd_b200 has no CPU or eager fallback.")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in EXPORTS.items():
+            fn = getattr(handle, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+def check(rc: int):
+    if rc != 0:
+        raise RuntimeError(f"libg4c error {rc}: {lib().g4c_last_error().decode()}")
+
+
+def launch_count() -> int:
+    return int(lib().g4c_launch_count())
+
+
+def ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda_f32(*tensors):
+    for t in tensors:
+        if t is None:
+            continue
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+            raise RuntimeError("graphs4cfd_b200 kernels need contiguous fp32 CUDA tensors "
+                               f"(got device={t.device}, dtype={t.dtype}, contiguous={t.is_contiguous()}); "
+                               "there is no CPU fallback")
+
+
+def host_guillard(senders: np.ndarray, n: int) -> np.ndarray:
+    senders = np.ascontiguousarray(senders, dtype=np.int64)
+    mask = np.empty(n, dtype=np.uint8)
+    check(lib().g4c_host_guillard(senders.ctypes.data_as(C.c_void_p), n, senders.shape[1],
+                                  mask.ctypes.data_as(C.c_void_p)))
+    return mask.astype(bool)

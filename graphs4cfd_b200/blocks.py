@@ -1,0 +1,344 @@
+"""Drop-in replacements for the block classes of graphs4cfd/nn/blocks.py.
+
+Same constructor arguments, same ``forward`` signatures and return values, same parameter names
+(``edge_mlp.MLP.linear_1.weight`` ... ``MLP.layer_norm.bias``) so ``state_dict()``, ``load_state_dict()``
+and the shipped ``.chk`` files work unchanged; the arithmetic runs in libg4c's fused sm_100a kernels.
+
+Two ways in:
+  * ``accelerate(model)`` swaps the blocks of an already-built reference model in place
+    (re-using its ``nn.Parameter`` objects);
+  * ``patch_reference(graphs4cfd)`` rebinds ``MLP/MP/DownMP/...`` in the reference's model modules so
+    models constructed afterwards are built from these classes.
+
+Inputs must be contiguous fp32 CUDA tensors; anything else raises (no CPU / eager fallback).
+Autograd is not supported (inference path): calling a block with grad-requiring inputs raises.
+"""
+from collections import OrderedDict
+from typing import Callable, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import ops
+from ._lib import require_cuda_f32
+
+_DEFAULT_PRECISION = "fp32"
+
+
+def _act_code(activation: Optional[Callable]):
+    """Fold torch.tanh / F.selu into the kernel epilogue; anything else is applied afterwards."""
+    if activation is None:
+        return None, None
+    if activation in (torch.tanh, F.tanh):
+        return "tanh", None
+    if activation in (F.selu, torch.selu):
+        return "selu", None
+    return None, activation
+
+
+def _no_grad_guard(*tensors):
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
+        raise RuntimeError("graphs4cfd_b200 blocks are forward-only; wrap the call in torch.no_grad() "
+                           "(GNN.solve already does)")
+
+
+class _Cache:
+    """Per-module cache of static plans keyed by the identity of the index tensors."""
+
+    def __init__(self):
+        self._d = {}
+
+    @staticmethod
+    def key(*tensors):
+        return tuple((t.data_ptr(), tuple(t.shape), t._version) for t in tensors)
+
+    def get(self, key, build):
+        hit = self._d.get(key)
+        if hit is None:
+            if len(self._d) > 16:
+                self._d.clear()
+            hit = self._d[key] = build()
+        return hit
+
+
+_TOPO_CACHE = _Cache()
+
+
+def _i32(t):
+    return _TOPO_CACHE.get(("i32",) + _Cache.key(t), lambda: t.to(torch.int32).contiguous())
+
+
+class MLP(nn.Module):
+    """Mirror of blocks.py:117-144.  ``self.MLP`` keeps the reference's layer names."""
+
+    def __init__(self, input_size: int, layers_width: Tuple[int], layer_norm: bool = False):
+        super().__init__()
+        widths = list(layers_width)
+        assert len(widths) >= 2, "an MLP needs at least two Linear layers"
+        layers = OrderedDict()
+        fan_in = input_size
+        for i, w in enumerate(widths, start=1):
+            layers[f"linear_{i}"] = nn.Linear(fan_in, w)
+            if i < len(widths):
+                layers[f"selu_{i}"] = nn.SELU()
+            fan_in = w
+        if layer_norm:
+            layers["layer_norm"] = nn.LayerNorm(widths[-1])
+        self.MLP = nn.Sequential(layers)
+        self._pack, self._pack_key = None, None
+
+    @classmethod
+    def adopt(cls, ref_mlp: nn.Module):
+        """Wrap an existing reference MLP, sharing its Sequential (and therefore its Parameters)."""
+        self = cls.__new__(cls)
+        nn.Module.__init__(self)
+        self.MLP = ref_mlp.MLP
+        self._pack, self._pack_key = None, None
+        return self
+
+    def pack(self) -> ops.MlpPack:
+        key = tuple((p.data_ptr(), p._version, str(p.device)) for p in self.MLP.parameters())
+        if self._pack is None or key != self._pack_key:
+            self._pack, self._pack_key = ops.MlpPack.from_module(self), key
+        return self._pack
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        require_cuda_f32(x)
+        _no_grad_guard(x)
+        return ops.rowmlp(self.pack(), [(x, None, 1.0)])
+
+
+class GNBlock(nn.Module):
+    """Mirror of blocks.py:147-186: returns the PRE-activation (v', e'); the caller's edge order is kept."""
+
+    def __init__(self, edge_mlp_args: Tuple, node_mlp_args: Tuple, aggr: str = 'mean'):
+        super().__init__()
+        self.edge_mlp = MLP(*edge_mlp_args)
+        self.node_mlp = MLP(*node_mlp_args)
+        self.aggr = aggr
+        self.precision = _DEFAULT_PRECISION
+
+    def forward(self, v: torch.Tensor, e: torch.Tensor, edge_index: torch.Tensor):
+        require_cuda_f32(v, e)
+        _no_grad_guard(v, e)
+        if self.aggr not in ("mean", "sum"):
+            raise RuntimeError(f"aggr={self.aggr!r} is not supported (mean, sum)")
+        topo = _TOPO_CACHE.get(("mp", v.size(0)) + _Cache.key(edge_index),
+                               lambda: ops.MpTopo.from_edge_index(edge_index, v.size(0)))
+        v_new, e_new = ops.mp(self.edge_mlp.pack(), self.node_mlp.pack(), topo, e, v, v,
+                              aggr=self.aggr, precision=self.precision)
+        return v_new, e_new
+
+
+MP = GNBlock
+
+
+def pooled_edges(idx_hr_to_lr: torch.Tensor, edge_index: torch.Tensor):
+    """Static half of pool_edge (blocks.py:51-68), computed once per mesh: coarse edge_index (sorted
+    row-major like coalesce) and the CSR (ptr, idx) of kept fine edges per coarse edge."""
+    num_nodes = int(idx_hr_to_lr.max()) + 1
+    ei = idx_hr_to_lr[edge_index.reshape(-1)].view(2, -1)
+    keep = (ei[0] != ei[1]).nonzero().squeeze(1)
+    key = ei[0, keep] * num_nodes + ei[1, keep]
+    order = torch.sort(key, stable=True).indices
+    uniq, counts = torch.unique_consecutive(key[order], return_counts=True)
+    ptr = torch.zeros(uniq.numel() + 1, dtype=torch.int64, device=key.device)
+    ptr[1:] = counts.cumsum(0)
+    ei_lr = torch.stack([uniq // num_nodes, uniq % num_nodes])
+    return ei_lr, ptr.to(torch.int32), keep[order].to(torch.int32)
+
+
+def children_csr(idx_hr_to_lr: torch.Tensor):
+    """CSR of fine nodes per coarse node (ascending fine id inside a group = scatter order)."""
+    n_l = int(idx_hr_to_lr.max()) + 1
+    order = torch.sort(idx_hr_to_lr, stable=True).indices
+    ptr = torch.zeros(n_l + 1, dtype=torch.int64, device=idx_hr_to_lr.device)
+    ptr[1:] = torch.bincount(idx_hr_to_lr, minlength=n_l).cumsum(0)
+    return n_l, ptr.to(torch.int32), order.to(torch.int32)
+
+
+class DownMP(nn.Module):
+    """Mirror of blocks.py:193-237 (mutates ``graph`` exactly like the reference)."""
+
+    def __init__(self, down_mlp_args: Tuple, hr_graph_idx: int):
+        super().__init__()
+        self.down_mlp = MLP(*down_mlp_args)
+        self.hr_graph_idx = hr_graph_idx
+        self.lr_graph_idx = hr_graph_idx + 1
+
+    def forward(self, graph, activation: Optional[Callable] = None):
+        h, l = self.hr_graph_idx, self.lr_graph_idx
+        idx = getattr(graph, f'idx{h}_to_idx{l}')
+        e_hl = getattr(graph, f'e_{h}{l}')
+        require_cuda_f32(graph.field, graph.edge_attr, e_hl)
+        _no_grad_guard(graph.field, graph.edge_attr)
+        graph.pos = getattr(graph, f'pos_{l}')
+        x = ops.rowmlp(self.down_mlp.pack(), [(e_hl, None, 1.0), (graph.field, None, 1.0)])
+        n_l, cptr, cidx = _TOPO_CACHE.get(("children",) + _Cache.key(idx), lambda: children_csr(idx))
+        code, post = _act_code(activation)
+        graph.field = ops.seg_reduce(x, cptr, cidx, n_l, "mean", code)
+        if post is not None:
+            graph.field = post(graph.field)
+        ei_l, eptr, eidx = _TOPO_CACHE.get(("pool",) + _Cache.key(idx, graph.edge_index),
+                                           lambda: pooled_edges(idx, graph.edge_index))
+        if ei_l.size(1) > 0:
+            graph.edge_attr = ops.seg_reduce(graph.edge_attr, eptr, eidx, ei_l.size(1), "mean", None)
+        else:
+            graph.edge_attr = graph.edge_attr[:0]
+        graph.edge_index = ei_l
+        return graph
+
+
+class UpMP(nn.Module):
+    """Mirror of blocks.py:240-290."""
+
+    def __init__(self, up_mlp_args: Tuple, lr_graph_idx: int):
+        super().__init__()
+        self.up_mlp = MLP(*up_mlp_args)
+        self.lr_graph_idx = lr_graph_idx
+        self.hr_graph_idx = lr_graph_idx - 1
+
+    def forward(self, graph, field_hr_old: torch.Tensor, pos_hr: torch.Tensor, activation: Optional[Callable] = None):
+        h, l = self.hr_graph_idx, self.lr_graph_idx
+        idx = getattr(graph, f'idx{h}_to_idx{l}')
+        e_hl = getattr(graph, f'e_{h}{l}')
+        require_cuda_f32(graph.field, field_hr_old, e_hl)
+        _no_grad_guard(graph.field, field_hr_old)
+        code, post = _act_code(activation)
+        graph.field = ops.rowmlp(self.up_mlp.pack(),
+                                 [(e_hl, None, -1.0), (graph.field, _i32(idx), 1.0), (field_hr_old, None, 1.0)],
+                                 rows=field_hr_old.size(0), act=code)
+        graph.pos = pos_hr
+        if post is not None:
+            graph.field = post(graph.field)
+        return graph
+
+
+class EdgeMP(nn.Module):
+    """Mirror of blocks.py:293-333: the same fused kernel with angles as rows and edges as targets."""
+
+    def __init__(self, angle_mlp_args: Tuple, edge_mlp_args: Tuple, aggr: str = "mean"):
+        super().__init__()
+        self.angle_mlp = MLP(*angle_mlp_args)
+        self.edge_mlp = MLP(*edge_mlp_args)
+        self.aggr = aggr
+        self.precision = _DEFAULT_PRECISION
+
+    def forward(self, e: torch.Tensor, a: torch.Tensor, angle_index: torch.Tensor):
+        require_cuda_f32(e, a)
+        _no_grad_guard(e, a)
+        topo = _TOPO_CACHE.get(("mp", e.size(0)) + _Cache.key(angle_index),
+                               lambda: ops.MpTopo.from_edge_index(angle_index, e.size(0)))
+        e_new, a_new = ops.mp(self.angle_mlp.pack(), self.edge_mlp.pack(), topo, a, e, e,
+                              aggr=self.aggr, precision=self.precision)
+        return e_new, a_new
+
+
+class DownEdgeMP(nn.Module):
+    """Mirror of blocks.py:336-381: senders are level-1 edges, receivers level-2 edges."""
+
+    def __init__(self, angle_mlp_args: Tuple, edge_mlp_args: Tuple):
+        super().__init__()
+        self.angle_mlp = MLP(*angle_mlp_args)
+        self.edge_mlp = MLP(*edge_mlp_args)
+        self.precision = _DEFAULT_PRECISION
+
+    def forward(self, e1, e2, a12, angle_index12):
+        require_cuda_f32(e1, e2, a12)
+        _no_grad_guard(e1, e2, a12)
+        topo = _TOPO_CACHE.get(("mp", e2.size(0)) + _Cache.key(angle_index12),
+                               lambda: ops.MpTopo.from_edge_index(angle_index12, e2.size(0)))
+        e2_new, _ = ops.mp(self.angle_mlp.pack(), self.edge_mlp.pack(), topo, a12, e1, e2,
+                           aggr="mean", want_e=False, precision=self.precision)
+        return e2_new
+
+
+def edgeScalarToNodeVector(edge_attr, edge_index, edgeUnitVector=None, edgeUnitVectorInverse=None, coarse_mask=None):
+    """Mirror of blocks.py:88-114 for the precomputed-inverse form the models use."""
+    assert (edgeUnitVector is None) != (edgeUnitVectorInverse is None), \
+        "Either edgeUnitVector or edgeUnitVectorInverse must be provided."
+    if edgeUnitVectorInverse is None:
+        num_nodes = int(edge_index.max()) + 1 if coarse_mask is None else int(coarse_mask.sum())
+        edgeUnitVectorInverse = torch.linalg.pinv(edgeUnitVector.view(num_nodes, -1, 2))
+    return ops.edge_to_node(edge_attr, edgeUnitVectorInverse.contiguous())
+
+
+class UpEdgeMP(nn.Module):
+    """Mirror of blocks.py:384-456."""
+
+    def __init__(self, up_mlp_args: Tuple):
+        super().__init__()
+        self.up_mlp = MLP(*up_mlp_args)
+
+    def forward(self, pos, y_idx_21, x_idx_21, weights_21, edge_attr2, edge_index2, edgeUnitVectorInverse2,
+                coarse_mask2, edge_attr1, edge_index1, edgeUnitVector1, coarse_mask1=None):
+        require_cuda_f32(edge_attr2, edge_attr1, edgeUnitVectorInverse2, edgeUnitVector1, weights_21)
+        _no_grad_guard(edge_attr2, edge_attr1)
+        total = pos.size(0)
+        v2 = ops.edge_to_node(edge_attr2, edgeUnitVectorInverse2)
+        n_y, k = _TOPO_CACHE.get(("interp",) + _Cache.key(y_idx_21),
+                                 lambda: (int(y_idx_21.max()) + 1, y_idx_21.numel() // (int(y_idx_21.max()) + 1)))
+        v1 = torch.zeros(total, v2.size(1), device=v2.device, dtype=torch.float32)
+        y_row = None
+        if coarse_mask1 is not None:
+            y_row = _TOPO_CACHE.get(("rows",) + _Cache.key(coarse_mask1),
+                                    lambda: coarse_mask1.nonzero().squeeze(1).to(torch.int32))
+        ops.interp(v2, _i32(x_idx_21), weights_21.reshape(-1), k, n_y, v1, y_row)
+        col1 = _TOPO_CACHE.get(("col",) + _Cache.key(edge_index1), lambda: edge_index1[1].to(torch.int32).contiguous())
+        e1 = ops.project(v1, col1, edgeUnitVector1)
+        return ops.rowmlp(self.up_mlp.pack(), [(e1, None, 1.0), (edge_attr1, None, 1.0)])
+
+
+# --------------------------------------------------------------------------- drop-in plumbing
+_BY_REF_NAME = {"MLP": MLP, "GNBlock": GNBlock, "DownMP": DownMP, "UpMP": UpMP, "EdgeMP": EdgeMP,
+                "DownEdgeMP": DownEdgeMP, "UpEdgeMP": UpEdgeMP}
+
+
+def _convert(mod: nn.Module, precision: str):
+    name = type(mod).__name__
+    if isinstance(mod, tuple(_BY_REF_NAME.values())):
+        return mod
+    if name == "MLP":
+        return MLP.adopt(mod)
+    cls = _BY_REF_NAME.get(name)
+    if cls is None:
+        return None
+    new = cls.__new__(cls)
+    nn.Module.__init__(new)
+    for attr in ("edge_mlp", "node_mlp", "angle_mlp", "down_mlp", "up_mlp"):
+        if hasattr(mod, attr):
+            setattr(new, attr, MLP.adopt(getattr(mod, attr)))
+    for attr in ("aggr", "hr_graph_idx", "lr_graph_idx"):
+        if hasattr(mod, attr):
+            setattr(new, attr, getattr(mod, attr))
+    if hasattr(new, "edge_mlp"):
+        new.precision = precision
+    return new
+
+
+def accelerate(model: nn.Module, precision: str = "fp32") -> nn.Module:
+    """Replace every graphs4cfd block of ``model`` by its libg4c counterpart, in place, keeping the
+    Parameters and state-dict keys.  ``model.forward``/``solve`` then run unchanged reference code
+    between fused blocks."""
+    import sys
+    for name, child in list(model.named_children()):
+        new = _convert(child, precision)
+        if new is not None and new is not child:
+            setattr(model, name, new)
+    mod = sys.modules.get(type(model).__module__)
+    if mod is not None and hasattr(mod, "edgeScalarToNodeVector"):
+        mod.edgeScalarToNodeVector = edgeScalarToNodeVector
+    return model
+
+
+def patch_reference(gfd) -> None:
+    """Rebind the block names inside the reference's model modules (they are looked up as module
+    globals when ``load_arch`` runs, nn/mus_gnn.py:7, nn/remus_gnn.py:7, nn/mugs_gnn.py:7)."""
+    for sub in ("mus_gnn", "remus_gnn", "mugs_gnn"):
+        m = getattr(gfd.nn, sub, None)
+        if m is None:
+            continue
+        for name in ("MLP", "MP", "DownMP", "UpMP", "EdgeMP", "DownEdgeMP", "UpEdgeMP", "edgeScalarToNodeVector"):
+            if hasattr(m, name):
+                setattr(m, name, globals()[name])

@@ -1,0 +1,43 @@
+// common.cuh — shared device helpers for libg4c (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/g4c.h"
+
+namespace g4c {
+
+constexpr float kSeluAlpha = 1.6732632423543772848170429916717f;
+constexpr float kSeluScale = 1.0507009873554804934193349852946f;
+constexpr float kLnEps = 1e-5f;
+
+// torch.nn.functional.selu / torch.tanh on fp32 (ATen: scale*(x>0 ? x : alpha*(exp(x)-1)))
+__device__ __forceinline__ float selu(float x) {
+    return x > 0.f ? kSeluScale * x : (kSeluScale * kSeluAlpha) * (expf(x) - 1.f);
+}
+__device__ __forceinline__ float apply_act(float x, int act) {
+    if (act == G4C_ACT_SELU) return selu(x);
+    if (act == G4C_ACT_TANH) return tanhf(x);
+    return x;
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// streaming 16B load that does not pollute L1 (row data is consumed once per CTA)
+__device__ __forceinline__ float4 ldg_stream(const float* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+int check_launch(const char* what);
+
+}  // namespace g4c

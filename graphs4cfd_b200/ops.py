@@ -1,0 +1,229 @@
+"""Tensor-level wrappers over the C ABI (include/g4c.h): PyTorch tensors in, PyTorch tensors out.
+PyTorch only owns the memory and the stream; every computation below is a libg4c kernel."""
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+
+
+class MlpPack:
+    """Device-resident weights of one reference ``MLP`` (graphs4cfd/nn/blocks.py:129-144) in the
+    layout the kernels read: every Linear transposed to [in, out] (a final layer narrower than 16
+    stays [out, in]); optional LayerNorm affine."""
+
+    def __init__(self, linears: Sequence[Tuple[torch.Tensor, torch.Tensor]], ln=None):
+        assert 2 <= len(linears) <= L.MAX_LAYERS, "MLP must have 2 or 3 Linear layers"
+        self.n_layers = len(linears)
+        self.in_width = int(linears[0][0].shape[1])
+        self.hidden = int(linears[0][0].shape[0])
+        self.out_width = int(linears[-1][0].shape[0])
+        for W, _ in linears[:-1]:
+            if W.shape[0] != self.hidden:
+                raise RuntimeError("graphs4cfd_b200: all hidden widths of an MLP must be equal")
+        self.W_t, self.b = [], []
+        for i, (W, b) in enumerate(linears):
+            W = W.detach().float()
+            narrow_last = (i == self.n_layers - 1) and self.out_width != self.hidden
+            self.W_t.append(W.contiguous().clone() if narrow_last else W.t().contiguous())
+            self.b.append(b.detach().float().contiguous().clone())
+        self.ln = None if ln is None else (ln[0].detach().float().contiguous().clone(),
+                                           ln[1].detach().float().contiguous().clone())
+        L.require_cuda_f32(*self.W_t, *self.b)
+        self._struct = None
+
+    @classmethod
+    def from_module(cls, mlp_module):
+        seq = mlp_module.MLP
+        linears, i = [], 1
+        while hasattr(seq, f"linear_{i}"):
+            lin = getattr(seq, f"linear_{i}")
+            linears.append((lin.weight, lin.bias))
+            i += 1
+        ln = (seq.layer_norm.weight, seq.layer_norm.bias) if hasattr(seq, "layer_norm") else None
+        return cls(linears, ln)
+
+    @classmethod
+    def from_state(cls, params, prefix, device):
+        linears, i = [], 1
+        while f"{prefix}.MLP.linear_{i}.weight" in params:
+            linears.append((params[f"{prefix}.MLP.linear_{i}.weight"].to(device),
+                            params[f"{prefix}.MLP.linear_{i}.bias"].to(device)))
+            i += 1
+        g = params.get(f"{prefix}.MLP.layer_norm.weight")
+        ln = None if g is None else (g.to(device), params[f"{prefix}.MLP.layer_norm.bias"].to(device))
+        return cls(linears, ln)
+
+    def struct(self) -> L.Mlp:
+        if self._struct is None:
+            m = L.Mlp()
+            m.n_layers, m.in_width, m.hidden, m.out_width = self.n_layers, self.in_width, self.hidden, self.out_width
+            for i in range(self.n_layers):
+                m.W_t[i] = self.W_t[i].data_ptr()
+                m.b[i] = self.b[i].data_ptr()
+            if self.ln is not None:
+                m.ln_gamma, m.ln_beta = self.ln[0].data_ptr(), self.ln[1].data_ptr()
+            self._struct = m
+        return self._struct
+
+
+class MpTopo:
+    """Static topology of one message-passing level in AGGREGATION order (edges sorted by target).
+    fixed_k > 0: target n owns slots [n*k, (n+1)*k) and the caller's order is already that order
+    (kNN graphs, transforms/connect.py:58); otherwise CSR ``rowptr`` + ``edge_perm`` (slot -> caller row)."""
+
+    def __init__(self, n_targets, n_edges, src, fixed_k=0, rowptr=None, edge_perm=None, tgt_perm=None):
+        self.n_targets, self.n_edges = int(n_targets), int(n_edges)
+        self.src, self.fixed_k, self.rowptr, self.edge_perm, self.tgt_perm = src, int(fixed_k), rowptr, edge_perm, tgt_perm
+
+    @classmethod
+    def from_edge_index(cls, edge_index: torch.Tensor, n_targets: int, device=None):
+        device = edge_index.device if device is None else device
+        row, col = edge_index[0], edge_index[1]
+        E = int(row.numel())
+        if E > 0 and n_targets > 0 and E % n_targets == 0:
+            k = E // n_targets
+            expect = torch.arange(n_targets, device=col.device).repeat_interleave(k)
+            if torch.equal(col, expect):
+                return cls(n_targets, E, row.to(device=device, dtype=torch.int32).contiguous(), fixed_k=k)
+        perm = torch.sort(col, stable=True).indices
+        counts = torch.bincount(col, minlength=n_targets)
+        rowptr = torch.zeros(n_targets + 1, dtype=torch.int64, device=col.device)
+        rowptr[1:] = counts.cumsum(0)
+        return cls(n_targets, E, row[perm].to(device=device, dtype=torch.int32).contiguous(),
+                   rowptr=rowptr.to(device=device, dtype=torch.int32).contiguous(),
+                   edge_perm=perm.to(device=device, dtype=torch.int32).contiguous())
+
+
+def _seg_struct(t: torch.Tensor, gather, scale) -> L.Seg:
+    s = L.Seg()
+    s.ptr, s.gather = t.data_ptr(), (0 if gather is None else gather.data_ptr())
+    s.width, s.stride, s.scale = int(t.shape[1]), int(t.stride(0)), float(scale)
+    return s
+
+
+def rowmlp(pack: MlpPack, segs, rows: Optional[int] = None, act=None, out=None, residual=None):
+    """out = act(MLP(cat(segs, dim=-1)) [+ residual]); segs = [(tensor[*, w], gather_idx|None, scale)]."""
+    d = L.RowMlpDesc()
+    tens = [s[0] for s in segs]
+    for t in tens:
+        if not (t.is_cuda and t.dtype == torch.float32 and t.stride(1) == 1):
+            raise RuntimeError("rowmlp: segments must be fp32 CUDA tensors with unit column stride")
+    if rows is None:
+        rows = int(segs[0][1].numel()) if segs[0][1] is not None else int(tens[0].shape[0])
+    d.rows, d.n_segs, d.act_out = rows, len(segs), L.ACTS[act]
+    for i, (t, gather, scale) in enumerate(segs):
+        d.seg[i] = _seg_struct(t, gather, scale)
+    d.mlp = pack.struct()
+    if out is None:
+        out = torch.empty(rows, pack.out_width, device=tens[0].device, dtype=torch.float32)
+    d.out, d.out_stride = out.data_ptr(), int(out.stride(0))
+    if residual is not None:
+        d.residual, d.res_stride = residual.data_ptr(), int(residual.stride(0))
+    L.check(L.lib().g4c_rowmlp_fwd(C.byref(d), L.stream_ptr()))
+    return out
+
+
+def mp(edge_pack: MlpPack, node_pack: MlpPack, topo: MpTopo, e_in, src_feat, tgt_feat, aggr="mean",
+       act_e=None, act_t=None, want_e=True, precision="fp32", e_out=None, t_out=None):
+    """Fused message-passing block (g4c_mp_fwd).  Returns (t_out, e_out|None)."""
+    L.require_cuda_f32(e_in, src_feat, tgt_feat)
+    H = edge_pack.hidden
+    d = L.MpDesc()
+    d.hidden, d.aggr, d.fixed_k = H, (L.AGGR_MEAN if aggr == "mean" else L.AGGR_SUM), topo.fixed_k
+    d.act_e_out, d.act_t_out, d.precision = L.ACTS[act_e], L.ACTS[act_t], L.PRECISIONS[precision]
+    d.n_targets, d.n_edges = topo.n_targets, topo.n_edges
+    d.rowptr = 0 if topo.rowptr is None else topo.rowptr.data_ptr()
+    d.src = topo.src.data_ptr()
+    d.edge_perm = 0 if topo.edge_perm is None else topo.edge_perm.data_ptr()
+    d.tgt_perm = 0 if topo.tgt_perm is None else topo.tgt_perm.data_ptr()
+    if want_e and e_out is None:
+        e_out = torch.empty(topo.n_edges, H, device=e_in.device, dtype=torch.float32)
+    if t_out is None:
+        t_out = torch.empty(tgt_feat.shape[0], H, device=e_in.device, dtype=torch.float32)
+    d.e_in, d.src_feat, d.tgt_feat = e_in.data_ptr(), src_feat.data_ptr(), tgt_feat.data_ptr()
+    d.e_out = e_out.data_ptr() if want_e else 0
+    d.t_out = t_out.data_ptr()
+    d.edge_mlp, d.node_mlp = edge_pack.struct(), node_pack.struct()
+    L.check(L.lib().g4c_mp_fwd(C.byref(d), L.stream_ptr()))
+    return t_out, (e_out if want_e else None)
+
+
+def seg_reduce(x, ptr, idx, n_groups, aggr="mean", act=None, out=None):
+    L.require_cuda_f32(x)
+    d = L.SegReduceDesc()
+    d.n_groups, d.width = int(n_groups), int(x.shape[1])
+    d.aggr, d.act_out = (L.AGGR_MEAN if aggr == "mean" else L.AGGR_SUM), L.ACTS[act]
+    d.ptr, d.idx, d.x = ptr.data_ptr(), (0 if idx is None else idx.data_ptr()), x.data_ptr()
+    if out is None:
+        out = torch.empty(n_groups, x.shape[1], device=x.device, dtype=torch.float32)
+    d.out = out.data_ptr()
+    L.check(L.lib().g4c_seg_reduce_fwd(C.byref(d), L.stream_ptr()))
+    return out
+
+
+def project(V, col, U, extras=(), out=None):
+    """(V[col].view(E,-1,2)*U.unsqueeze(1)).sum(-1) with per-node scalars appended."""
+    L.require_cuda_f32(V, U, *extras)
+    d = L.ProjectDesc()
+    F = int(V.shape[1]) // 2
+    d.n_edges, d.n_feat, d.n_extra = int(col.numel()), F, len(extras)
+    d.col, d.V, d.U = col.data_ptr(), V.data_ptr(), U.data_ptr()
+    for i, x in enumerate(extras):
+        d.extra[i] = x.data_ptr()
+    if out is None:
+        out = torch.empty(col.numel(), F + len(extras), device=V.device, dtype=torch.float32)
+    d.out = out.data_ptr()
+    L.check(L.lib().g4c_project_fwd(C.byref(d), L.stream_ptr()))
+    return out
+
+
+def edge_to_node(e, Uinv, out=None, residual=None):
+    """edgeScalarToNodeVector with the precomputed pseudo-inverse: [N*k,F] -> [N,2F]."""
+    L.require_cuda_f32(e, Uinv)
+    d = L.EdgeToNodeDesc()
+    n, _, k = Uinv.shape
+    d.n_nodes, d.k, d.n_feat = int(n), int(k), int(e.shape[1])
+    d.Uinv, d.e = Uinv.data_ptr(), e.data_ptr()
+    if out is None:
+        out = torch.empty(n, 2 * e.shape[1], device=e.device, dtype=torch.float32)
+    d.V, d.out_stride = out.data_ptr(), int(out.stride(0))
+    if residual is not None:
+        d.residual, d.res_stride = residual.data_ptr(), int(residual.stride(0))
+    L.check(L.lib().g4c_edge_to_node_fwd(C.byref(d), L.stream_ptr()))
+    return out
+
+
+def interp(x, x_idx, w, k, n_out, y, y_row=None):
+    L.require_cuda_f32(x, w, y)
+    d = L.InterpDesc()
+    d.n_out, d.k, d.width = int(n_out), int(k), int(x.shape[1])
+    d.x_idx, d.w, d.x, d.y = x_idx.data_ptr(), w.data_ptr(), x.data_ptr(), y.data_ptr()
+    d.y_row = 0 if y_row is None else y_row.data_ptr()
+    L.check(L.lib().g4c_interp_fwd(C.byref(d), L.stream_ptr()))
+    return y
+
+
+def step_update(pred, node_in, field_width, outputs, t):
+    d = L.StepUpdateDesc()
+    d.n_nodes, d.nf, d.field_width = int(pred.shape[0]), int(pred.shape[1]), int(field_width)
+    d.in_stride, d.out_stride, d.t = int(node_in.stride(0)), int(outputs.stride(0)), int(t)
+    d.pred, d.node_in, d.outputs = pred.data_ptr(), node_in.data_ptr(), outputs.data_ptr()
+    L.check(L.lib().g4c_step_update(C.byref(d), L.stream_ptr()))
+
+
+def halo_pack(src, idx, dst):
+    d = L.HaloDesc()
+    d.n_rows, d.width = int(idx.numel()), int(src.shape[1])
+    d.idx, d.src, d.dst = idx.data_ptr(), src.data_ptr(), dst.data_ptr()
+    L.check(L.lib().g4c_halo_pack(C.byref(d), L.stream_ptr()))
+    return dst
+
+
+def halo_unpack(buf, idx, dst):
+    d = L.HaloDesc()
+    d.n_rows, d.width = int(idx.numel()), int(dst.shape[1])
+    d.idx, d.src, d.dst = idx.data_ptr(), buf.data_ptr(), dst.data_ptr()
+    L.check(L.lib().g4c_halo_unpack(C.byref(d), L.stream_ptr()))
+    return dst

@@ -1,0 +1,251 @@
+"""Rollout engine: ``Rollout(model_or_state_dict, graph).solve(n_out)`` == ``GNN.solve`` (nn/model.py:303-321).
+
+At construction the engine turns (state_dict, static mesh attributes) into a plan:
+  * the block program (program.py) with the model-level ``F.selu``/``tanh`` folded into kernel epilogues
+    (nn/mus_gnn.py:317-367) and discarded edge outputs never written (nn/mus_gnn.py:346,354,366);
+  * every level's topology in aggregation order (fixed-k level 1; CSR coarse levels stored sorted by
+    target, so no permutation is needed inside the rollout), pooled-edge and children CSRs
+    (the per-step ``coalesce`` sort and ``.item()`` syncs of blocks.py:45,63,109 disappear);
+  * the static encoders evaluated once (edge encoder of MuS, nn/mus_gnn.py:317; angle encoders of REMuS,
+    nn/remus_gnn.py:136-140);
+  * pre-allocated, liveness-shared activation buffers, and one CUDA graph of a whole time step.
+``solve`` then replays the graph n_out times; nothing returns to the host inside the loop.
+"""
+from typing import Dict, List, Optional
+
+import torch
+
+from . import ops
+from .blocks import children_csr, pooled_edges
+from .program import block_program, hidden_width, is_remus
+
+
+def _state_of(model_or_params) -> Dict[str, torch.Tensor]:
+    if isinstance(model_or_params, dict):
+        return model_or_params
+    return {k: v.detach() for k, v in model_or_params.state_dict().items()}
+
+
+class _Pool:
+    """Shape-keyed free list: buffers are handed out at plan time, released at last use."""
+
+    def __init__(self, device):
+        self.device, self.free, self.bytes = device, {}, 0
+
+    def take(self, rows, width):
+        lst = self.free.setdefault((rows, width), [])
+        if lst:
+            return lst.pop()
+        self.bytes += rows * width * 4
+        return torch.empty(rows, width, device=self.device, dtype=torch.float32)
+
+    def give(self, t):
+        self.free.setdefault((t.shape[0], t.shape[1]), []).append(t)
+
+
+class _Level:
+    """Static data of one MuS level."""
+
+    def __init__(self):
+        self.n = 0
+        self.topo: Optional[ops.MpTopo] = None
+        self.e_hl = None        # relative position to the parent cell [n, 2]  (e_{l,l+1})
+        self.parent = None      # int32 [n] parent id at level l+1
+        self.children = None    # (ptr, idx) CSR of this level's nodes per parent
+        self.pool = None        # (ptr, idx, n_coarse_edges) CSR of this level's edges per coarse edge
+
+
+class Rollout:
+    def __init__(self, model_or_params, graph, precision: str = "fp32", device="cuda", cuda_graph: bool = True):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("Rollout needs a CUDA device; graphs4cfd_b200 has no CPU path")
+        self.params = {k: v.to(self.device) for k, v in _state_of(model_or_params).items()}
+        self.precision = precision
+        self.H = hidden_width(self.params)
+        self.prog = block_program(self.params)
+        self.packs = {}
+        self.use_graph = cuda_graph
+        self._graph = None
+        self.launches_per_step = 0
+        if is_remus(self.params):
+            from .rollout_remus import plan_remus
+            plan_remus(self, graph)
+        else:
+            self._plan_mus(graph)
+
+    # ------------------------------------------------------------------ helpers
+    def pack(self, prefix) -> ops.MlpPack:
+        p = self.packs.get(prefix)
+        if p is None:
+            p = self.packs[prefix] = ops.MlpPack.from_state(self.params, prefix, self.device)
+        return p
+
+    def _dev(self, t, dtype=None):
+        t = t.to(self.device)
+        if dtype is not None:
+            t = t.to(dtype)
+        return t.contiguous()
+
+    # ------------------------------------------------------------------ MuS plan
+    def _plan_mus(self, g):
+        dev = self.device
+        node_parts = [getattr(g, a) for a in ("field", "loc", "glob", "omega") if hasattr(g, a)]
+        self.field_width = int(g.field.shape[1])
+        self.node_in = self._dev(torch.cat([p.float() for p in node_parts], dim=1))
+        self.field0 = self.node_in[:, :self.field_width].clone()
+        self.N = int(self.node_in.shape[0])
+        self.nf = int(self.pack("node_decoder").out_width)
+
+        # ---- levels
+        n_down = sum(1 for _, k in self.prog if k == "down")
+        levels: List[_Level] = []
+        ei = g.edge_index.to(dev)
+        lv = _Level()
+        lv.n = self.N
+        lv.topo = ops.MpTopo.from_edge_index(ei, self.N)
+        levels.append(lv)
+        # static edge encoder output in level-1 aggregation order
+        ea = self._dev(g.edge_attr.float())
+        if lv.topo.edge_perm is not None:
+            ea = ea[lv.topo.edge_perm.long()].contiguous()
+            ei = ei[:, lv.topo.edge_perm.long()]
+            lv.topo.edge_perm = None
+        self.e0 = ops.rowmlp(self.pack("edge_encoder"), [(ea, None, 1.0)], act="selu")
+        for l in range(1, n_down + 1):
+            idx = getattr(g, f"idx{l}_to_idx{l + 1}").to(dev)
+            cur = levels[-1]
+            cur.e_hl = self._dev(getattr(g, f"e_{l}{l + 1}").float())
+            cur.parent = idx.to(torch.int32).contiguous()
+            n_l, cptr, cidx = children_csr(idx)
+            cur.children = (cptr, cidx)
+            ei_l, eptr, eidx = pooled_edges(idx, ei)
+            # store coarse edges sorted by target: aggregation order == storage order
+            order = torch.sort(ei_l[1], stable=True).indices
+            counts = (eptr[1:] - eptr[:-1]).long()[order]
+            new_ptr = torch.zeros(order.numel() + 1, dtype=torch.int64, device=dev)
+            new_ptr[1:] = counts.cumsum(0)
+            starts = eptr[:-1].long()[order]
+            gather = torch.repeat_interleave(starts - new_ptr[:-1], counts) + torch.arange(int(new_ptr[-1]), device=dev)
+            cur.pool = (new_ptr.to(torch.int32), eidx[gather].contiguous(), int(order.numel()))
+            ei = ei_l[:, order]
+            nxt = _Level()
+            nxt.n = n_l
+            nxt.topo = ops.MpTopo.from_edge_index(ei, n_l)
+            assert nxt.topo.edge_perm is None or torch.equal(nxt.topo.edge_perm.long(), torch.arange(ei.size(1), device=dev))
+            nxt.topo.edge_perm = None
+            levels.append(nxt)
+        self.levels = levels
+
+        # ---- step program with static buffer assignment (liveness-shared)
+        body = [(n, k) for n, k in self.prog if k != "mlp"]
+        pool = _Pool(dev)
+        H = self.H
+        steps = []
+        v = pool.take(self.N, H)
+        steps.append(("rowmlp", dict(pack=self.pack("node_encoder"), segs=[(self.node_in, None, 1.0)], act="selu", out=v)))
+        e = self.e0                      # static: never released, never written
+        level = 0
+        saved = {}
+        for i, (name, kind) in enumerate(body):
+            nxt = body[i + 1][1] if i + 1 < len(body) else "decoder"
+            L = levels[level]
+            if kind == "mp":
+                want_e = nxt not in ("up", "decoder")
+                v_new = pool.take(L.n, H)
+                e_new = pool.take(L.topo.n_edges, H) if want_e else None
+                steps.append(("mp", dict(ep=self.pack(name + ".edge_mlp"), np_=self.pack(name + ".node_mlp"), topo=L.topo,
+                                         e_in=e, v_in=v, e_out=e_new, v_out=v_new)))
+                pool.give(v)
+                if e is not self.e0 and not any(e is s[1] for s in saved.values()):
+                    pool.give(e)
+                v, e = v_new, e_new
+            elif kind == "down":
+                saved[level] = (v, e)
+                x = pool.take(L.n, H)
+                steps.append(("rowmlp", dict(pack=self.pack(name + ".down_mlp"), segs=[(L.e_hl, None, 1.0), (v, None, 1.0)],
+                                             act=None, out=x)))
+                nl = levels[level + 1]
+                v_l = pool.take(nl.n, H)
+                steps.append(("seg", dict(x=x, ptr=L.children[0], idx=L.children[1], n=nl.n, act="tanh", out=v_l)))
+                pool.give(x)
+                e_l = pool.take(L.pool[2], H)
+                steps.append(("seg", dict(x=e, ptr=L.pool[0], idx=L.pool[1], n=L.pool[2], act=None, out=e_l)))
+                v, e = v_l, e_l
+                level += 1
+            elif kind == "up":
+                v_old, e_old = saved.pop(level - 1)
+                Lh = levels[level - 1]
+                v_new = pool.take(Lh.n, H)
+                steps.append(("rowmlp", dict(pack=self.pack(name + ".up_mlp"),
+                                             segs=[(Lh.e_hl, None, -1.0), (v, Lh.parent, 1.0), (v_old, None, 1.0)],
+                                             act="tanh", out=v_new, rows=Lh.n)))
+                pool.give(v)
+                pool.give(v_old)
+                if e is not None:
+                    pool.give(e)
+                v, e = v_new, e_old
+                level -= 1
+            else:
+                raise ValueError(f"unexpected block kind {kind} in a MuS-GNN")
+        self.pred = torch.empty(self.N, self.nf, device=dev, dtype=torch.float32)
+        resid = self.node_in[:, self.field_width - self.nf:self.field_width]
+        steps.append(("rowmlp", dict(pack=self.pack("node_decoder"), segs=[(v, None, 1.0)], act=None, out=self.pred,
+                                     residual=resid)))
+        self.steps = steps
+        self.buffer_bytes = pool.bytes
+        self.launches_per_step = len(steps) + 1      # + step_update
+
+    # ------------------------------------------------------------------ execution
+    def _run_step_eager(self):
+        for op, a in self.steps:
+            if op == "rowmlp":
+                ops.rowmlp(a["pack"], a["segs"], rows=a.get("rows"), act=a["act"], out=a["out"], residual=a.get("residual"))
+            elif op == "mp":
+                ops.mp(a["ep"], a["np_"], a["topo"], a["e_in"], a.get("s_in", a["v_in"]), a["v_in"],
+                       aggr=a.get("aggr", "mean"), act_e="selu", act_t="selu",
+                       want_e=a["e_out"] is not None, precision=self.precision, e_out=a["e_out"], t_out=a["v_out"])
+            elif op == "seg":
+                ops.seg_reduce(a["x"], a["ptr"], a["idx"], a["n"], "mean", a["act"], out=a["out"])
+            elif op == "call":
+                a["fn"]()
+            else:
+                raise ValueError(op)
+
+    def _step(self):
+        if not self.use_graph:
+            self._run_step_eager()
+            return
+        if self._graph is None:
+            # warm up on a side stream (lazy CUDA init, cudaFuncSetAttribute) before capture
+            s = torch.cuda.Stream(device=self.device)
+            s.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(s):
+                self._run_step_eager()
+            torch.cuda.current_stream(self.device).wait_stream(s)
+            torch.cuda.synchronize(self.device)
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self._run_step_eager()
+        self._graph.replay()
+
+    def set_field(self, field: torch.Tensor):
+        """Load a new initial field [N, nf*n_in] (host or device)."""
+        self.node_in[:, :self.field_width].copy_(field.to(self.device, torch.float32))
+
+    def solve(self, n_out: int, field: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Roll the model out for n_out steps; returns [N, nf*n_out] on the device (original node order).
+        The engine's own input state is restored afterwards, like GNN.solve restores graph.field."""
+        assert n_out > 0, "n_out must be greater than 0."
+        with torch.no_grad(), torch.cuda.device(self.device):
+            self.set_field(self.field0 if field is None else field)
+            outputs = torch.empty(self.N, self.nf * n_out, device=self.device, dtype=torch.float32)
+            for t in range(n_out):
+                self._step()
+                ops.step_update(self.pred, self.node_in, self.field_width, outputs, t)
+            self.set_field(self.field0)
+        return outputs
+
+    def step_only(self):
+        """One time step without the output bookkeeping (used by the benchmark's timed loop)."""
+        self._step()

@@ -1,0 +1,222 @@
+/* g4c.h — C ABI of libg4c.so: the B200 (sm_100a) message-passing hot path of graphs4cfd.
+ *
+ * The reference (mario-linov/graphs4cfd) is pure Python and has no FFI of its own; its
+ * boundary for this path is the Python class API of graphs4cfd/nn/blocks.py.  Each entry
+ * point below names the reference interface it replaces (paths relative to the reference
+ * root).  The Python mirror of that class API lives in graphs4cfd_b200/blocks.py and calls
+ * these functions through ctypes (see INTEGRATION.md for the binding a maintainer adds).
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is a DEVICE pointer unless it says host
+ *  - feature matrices are row-major fp32 [rows, H]; index arrays are int32
+ *  - the library never allocates, frees or retains device memory; nothing synchronises
+ *  - every kernel is launched on the cudaStream_t passed as `void* stream` (CUDA-graph capturable)
+ *  - return 0 on success, a G4C_E* code otherwise; g4c_last_error() gives the text (thread local)
+ *  - weights: W_t[l] is the TRANSPOSE of torch's nn.Linear.weight, i.e. row-major [in_l, out_l],
+ *    EXCEPT a final layer narrower than 16 outputs, which stays in torch layout [out, in]
+ */
+#ifndef G4C_H
+#define G4C_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define G4C_VERSION 100
+
+#if defined(__GNUC__)
+#define G4C_API __attribute__((visibility("default")))
+#else
+#define G4C_API
+#endif
+
+enum { G4C_OK = 0, G4C_EINVAL = 1, G4C_EUNSUPPORTED = 2, G4C_ECUDA = 3 };
+enum { G4C_ACT_NONE = 0, G4C_ACT_SELU = 1, G4C_ACT_TANH = 2 };
+enum { G4C_AGGR_MEAN = 0, G4C_AGGR_SUM = 1 };
+/* arithmetic of the dense layers */
+enum { G4C_PREC_FP32 = 0,     /* fp32 FFMA on CUDA cores: exact-fp32 parity path            */
+       G4C_PREC_FP16X3 = 1,   /* tcgen05 tensor cores, operands split hi+lo fp16, 3 MMAs    */
+       G4C_PREC_BF16 = 2 };   /* tcgen05 single pass bf16 (fast, NOT within parity tolerance) */
+
+#define G4C_MAX_LAYERS 3
+#define G4C_MAX_SEGS 3
+
+/* One reference `MLP` (graphs4cfd/nn/blocks.py:129-144): Linear+SELU chain, optional LayerNorm
+ * (eps 1e-5, affine) after the last Linear.  Hidden widths must all equal `hidden`. */
+typedef struct {
+    int32_t n_layers;                 /* 2 or 3 (number of nn.Linear)                         */
+    int32_t in_width;                 /* K of linear_1 = sum of the concatenated segments     */
+    int32_t hidden;                   /* H: width of every layer but possibly the last        */
+    int32_t out_width;                /* width of the last layer (== hidden, or < 16)         */
+    const float* W_t[G4C_MAX_LAYERS]; /* see "weights" above                                  */
+    const float* b[G4C_MAX_LAYERS];
+    const float* ln_gamma;            /* NULL = no layer_norm                                 */
+    const float* ln_beta;
+} G4cMlp;
+
+/* One input segment of a concatenation `torch.cat((seg0, seg1, ...), dim=-1)`. */
+typedef struct {
+    const float* ptr;                 /* [*, width] rows, row stride `stride` floats          */
+    const int32_t* gather;            /* NULL: row r of the tile reads row r; else gather[r]  */
+    int32_t width;
+    int32_t stride;
+    float scale;                      /* multiplies the segment (UpMP uses -1 on e_hl)        */
+    int32_t _pad;
+} G4cSeg;
+
+/* out = act( MLP( cat(segs) ) ) over `rows` rows.
+ * Replaces: MLP.forward (blocks.py:143) as used for encoders/decoders (nn/mus_gnn.py:317-318,369;
+ * nn/remus_gnn.py:132-140,195), the MLP of DownMP (blocks.py:229), UpMP (blocks.py:285) and
+ * UpEdgeMP (blocks.py:456).  Optional `residual` ([rows, out_width], stride res_stride) is added
+ * after the MLP (nn/mus_gnn.py:373). */
+typedef struct {
+    int64_t rows;
+    int32_t n_segs;
+    int32_t act_out;
+    G4cSeg seg[G4C_MAX_SEGS];
+    G4cMlp mlp;
+    float* out;                       /* [rows, out_width], row stride out_stride floats      */
+    int32_t out_stride;
+    int32_t res_stride;
+    const float* residual;            /* NULL or [rows, >=out_width]                          */
+} G4cRowMlpDesc;
+
+/* Fused message-passing block:
+ *   e' = edge_mlp( cat(e, S[src], T[tgt]) );  agg = aggr_{edges of tgt} e';  t' = node_mlp( cat(agg, T) )
+ * Replaces: GNBlock.forward (blocks.py:175-186; S = T = v), EdgeMP.forward (blocks.py:322-333; rows are
+ * angles, S = T = e), DownEdgeMP.forward (blocks.py:360-381; S = e1, T = e2, e' not returned).
+ * Edges are consumed in AGGREGATION order: sorted by target; target n owns slots
+ * [rowptr[n], rowptr[n+1]) or, with fixed_k > 0, [n*k, (n+1)*k).  `edge_perm`/`tgt_perm` map an
+ * aggregation-order slot / target to its storage row (NULL = identity) so callers keep the
+ * reference's own edge order at the API boundary.  act_* fold the model-level F.selu that
+ * follows every block (nn/mus_gnn.py:321) into the store; agg always uses the un-activated e'. */
+typedef struct {
+    int32_t hidden;
+    int32_t aggr;
+    int32_t fixed_k;
+    int32_t act_e_out;
+    int32_t act_t_out;
+    int32_t precision;
+    int64_t n_targets;
+    int64_t n_edges;
+    const int32_t* rowptr;            /* [n_targets+1] when fixed_k == 0                      */
+    const int32_t* src;               /* [n_edges] source row (in S) per aggregation slot     */
+    const int32_t* edge_perm;         /* [n_edges] or NULL                                    */
+    const int32_t* tgt_perm;          /* [n_targets] or NULL                                  */
+    const float* e_in;                /* [n_edges, H]                                         */
+    const float* src_feat;            /* S [*, H]                                             */
+    const float* tgt_feat;            /* T [n_targets, H]                                     */
+    float* e_out;                     /* [n_edges, H] or NULL (edge output discarded)         */
+    float* t_out;                     /* [n_targets, H]                                       */
+    G4cMlp edge_mlp;                  /* in_width = 3H                                        */
+    G4cMlp node_mlp;                  /* in_width = 2H                                        */
+} G4cMpDesc;
+
+/* out[g] = act( reduce_{i in [ptr[g], ptr[g+1])} x[idx[i]] )   (idx NULL = identity)
+ * Replaces: scatter(...,'mean')[mask] + activation of DownMP (blocks.py:231-233) and the dynamic half
+ * of pool_edge/coalesce (blocks.py:64-67) once the pooled topology is cached at plan time. */
+typedef struct {
+    int64_t n_groups;
+    int32_t width;
+    int32_t aggr;
+    int32_t act_out;
+    int32_t _pad;
+    const int32_t* ptr;
+    const int32_t* idx;
+    const float* x;
+    float* out;
+} G4cSegReduceDesc;
+
+/* REMuS geometry helpers (all rows are fixed-k grouped by node):
+ * project:  out[j, f] = V[col[j], 2f]*U[j,0] + V[col[j], 2f+1]*U[j,1]  for f < F, then the `extra`
+ *           per-node scalars glob[col[j]], omega[col[j]] appended (nn/remus_gnn.py:124-130, blocks.py:453-454)
+ * edge_to_node: V[n, 2f+c] = sum_m Uinv[n, c, m] * e[n*k+m, f]            (blocks.py:88-114)
+ * interp:   y[i] = sum_m w[i*k+m]*x[x_idx[i*k+m]] / sum_m w[i*k+m], scattered to row y_row[i] of a
+ *           zero-filled output (blocks.py:34-48, 443-451) */
+typedef struct {
+    int64_t n_edges;
+    int32_t n_feat;                   /* F: V has 2F columns                                  */
+    int32_t n_extra;                  /* 0..2 extra per-node scalars                          */
+    const int32_t* col;               /* [n_edges] node row in V / extra                      */
+    const float* V;                   /* [*, 2F]                                              */
+    const float* U;                   /* [n_edges, 2]                                         */
+    const float* extra[2];            /* [*, 1] each                                          */
+    float* out;                       /* [n_edges, F + n_extra]                               */
+} G4cProjectDesc;
+
+typedef struct {
+    int64_t n_nodes;
+    int32_t k;
+    int32_t n_feat;
+    const float* Uinv;                /* [n_nodes, 2, k]                                      */
+    const float* e;                   /* [n_nodes*k, F]                                       */
+    float* V;                         /* [n_nodes, 2F], row stride out_stride                 */
+    int32_t out_stride;
+    int32_t res_stride;
+    const float* residual;            /* optional [n_nodes, >=2F]: V = residual + ...         */
+} G4cEdgeToNodeDesc;
+
+typedef struct {
+    int64_t n_out;                    /* interpolated rows                                    */
+    int32_t k;
+    int32_t width;
+    const int32_t* x_idx;             /* [n_out*k]                                            */
+    const float* w;                   /* [n_out*k]                                            */
+    const int32_t* y_row;             /* [n_out] destination row or NULL (identity)           */
+    const float* x;                   /* [*, width]                                           */
+    float* y;                         /* [*, width]                                           */
+} G4cInterpDesc;
+
+/* Rollout state update (GNN.solve + shift_and_replace, nn/model.py:316-327):
+ * outputs[:, t*nf:(t+1)*nf] = pred; field = cat(field[:, nf:], pred).  `field` is the first
+ * field_width columns of the node-input matrix (row stride in_stride). */
+typedef struct {
+    int64_t n_nodes;
+    int32_t nf;
+    int32_t field_width;
+    int32_t in_stride;
+    int32_t out_stride;
+    int32_t t;
+    int32_t _pad;
+    const float* pred;                /* [n_nodes, nf]                                        */
+    float* node_in;
+    float* outputs;                   /* [n_nodes, out_stride]                                */
+} G4cStepUpdateDesc;
+
+/* Halo exchange staging for the node-range partition (no reference counterpart: the reference
+ * is single-device).  pack: buf[i] = x[idx[i]];  unpack: x[idx[i]] = buf[i]. */
+typedef struct {
+    int64_t n_rows;
+    int32_t width;
+    int32_t _pad;
+    const int32_t* idx;
+    const float* src;
+    float* dst;
+} G4cHaloDesc;
+
+G4C_API int g4c_version(void);
+G4C_API const char* g4c_last_error(void);
+
+G4C_API int g4c_rowmlp_fwd(const G4cRowMlpDesc* d, void* stream);
+G4C_API int g4c_mp_fwd(const G4cMpDesc* d, void* stream);
+G4C_API int g4c_seg_reduce_fwd(const G4cSegReduceDesc* d, void* stream);
+G4C_API int g4c_project_fwd(const G4cProjectDesc* d, void* stream);
+G4C_API int g4c_edge_to_node_fwd(const G4cEdgeToNodeDesc* d, void* stream);
+G4C_API int g4c_interp_fwd(const G4cInterpDesc* d, void* stream);
+G4C_API int g4c_step_update(const G4cStepUpdateDesc* d, void* stream);
+G4C_API int g4c_halo_pack(const G4cHaloDesc* d, void* stream);
+G4C_API int g4c_halo_unpack(const G4cHaloDesc* d, void* stream);
+
+/* number of kernels this library has launched since load (bench.py reports it as gpu_launches) */
+G4C_API int64_t g4c_launch_count(void);
+
+/* host-side plan helper (HOST pointers): Guillard node-nested coarsening, the sequential sweep of
+ * transforms/mugs.py:8-29.  senders = int64 [n, k]; coarse_mask = uint8 [n] (out). */
+G4C_API int g4c_host_guillard(const int64_t* senders, int64_t n, int32_t k, uint8_t* coarse_mask);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* G4C_H */
