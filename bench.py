@@ -1,0 +1,293 @@
+#!/usr/bin/env python
+"""bench.py — rollout steps/s of the B200 message-passing hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm   (torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K ...  # reference arm: the CPU path (oracle port)
+
+One "step" = one rollout time step (`GNN.forward` + `shift_and_replace`, nn/model.py:316-320) of the
+3-scale MuS-GNN on a synthetic mesh.  Workload at any N: the 1M-node / 6M-edge mesh, hidden=128, that
+BASELINE.json's metric is quoted on (it fits one GPU), node-partitioned over N GPUs (strong scaling).
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="g4c", choices=["g4c", "reference"])
+    ap.add_argument("--nodes", type=int, default=1_000_000)
+    ap.add_argument("--hidden", type=int, default=128)
+    ap.add_argument("--k", type=int, default=6)
+    ap.add_argument("--levels", type=int, default=3)
+    ap.add_argument("--precision", default=os.environ.get("G4C_PRECISION", "fp32"))
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--cpu-sample-nodes", type=int, default=50_000)
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return f"mus{a.levels}-gnn rollout step, {a.nodes}-node/{a.nodes * a.k}-edge synthetic kNN mesh, hidden={a.hidden}"
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.2] or [r for _, r in self.rows]
+        sm, smax, reasons = [], None, set()
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                smax = float(r[2])
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def cpu_steps_per_s(a, steps, warmup, sample_nodes):
+    """Oracle port (reference op sequence in plain torch, all host threads) on a bounded sample of the
+    workload: the same model on a `sample_nodes` mesh; steps/s scaled linearly in N to the full mesh
+    (the reference's cost is linear in nodes/edges: BASELINE.md §2)."""
+    from graphs4cfd_b200 import mesh as M
+    from graphs4cfd_b200.archs import init_params, mus_arch
+    from oracle import restate as R
+    torch.set_num_threads(os.cpu_count() or 1)
+    n = min(sample_nodes, a.nodes)
+    g = M.build_mus_mesh(n, a.k, M.auto_cells(n, a.levels), seed=0)
+    params = init_params(mus_arch(a.hidden, a.levels), seed=0)
+    with torch.no_grad():
+        for _ in range(warmup):
+            R.forward(params, g)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            pred = R.forward(params, g)
+            g.field = torch.cat([g.field[:, pred.size(1):], pred], dim=1)
+        dt = (time.perf_counter() - t0) / steps
+    scale = n / a.nodes
+    return {"value": (1.0 / dt) * scale, "unit": "steps/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{steps} steps of the same {a.levels}-scale MuS-GNN (hidden={a.hidden}) on a {n}-node mesh, "
+                      f"{dt:.3f} s/step measured; steps/s scaled x{scale:.4g} (linear in nodes) to {a.nodes} nodes"}, dt / scale
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(a.steps, 3)), max(1, min(a.warmup, 1))
+    cb, s_per_step = cpu_steps_per_s(a, steps, warmup, a.cpu_sample_nodes)
+    line = {"impl": "reference", "metric": "rollout_steps_per_s", "value": cb["value"], "unit": "steps/s",
+            "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": s_per_step * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(a), "parallelism": "host cores", "timed_steps_on_sample": steps},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_g4c(a):
+    import torch.distributed as dist
+    from graphs4cfd_b200 import Rollout, ops
+    from graphs4cfd_b200 import mesh as M
+    from graphs4cfd_b200.archs import init_params, mus_arch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    g = M.build_mus_mesh(a.nodes, a.k, M.auto_cells(a.nodes, a.levels), seed=0)
+    params = init_params(mus_arch(a.hidden, a.levels), seed=0)
+    if world > 1:
+        from graphs4cfd_b200.partition import PartitionedRollout
+        eng = PartitionedRollout(params, g, rank=rank, world=world, precision=a.precision, device=dev,
+                                 cuda_graph=not a.no_graph)
+    else:
+        eng = Rollout(params, g, precision=a.precision, device=dev, cuda_graph=not a.no_graph)
+    N_local, nf, fw = eng.N, eng.nf, eng.field_width
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    outputs = torch.empty(N_local, nf * (a.steps + a.warmup), device=dev)
+
+    def one_step(t):
+        eng.step_only()
+        ops.step_update(eng.pred, eng.node_in, fw, outputs, t)
+
+    # ---- device-resident throughput
+    for t in range(a.warmup):
+        one_step(t)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    t_wall0 = time.time()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = ops.L.launch_count()
+    barrier()
+    ev0.record()
+    for t in range(a.steps):
+        one_step(a.warmup + t)
+    ev1.record()
+    barrier()
+    t_wall1 = time.time()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    launches = ops.L.launch_count() - launches0
+    if not a.no_graph:
+        launches = a.steps * eng.launches_per_step
+    if world > 1:
+        tms = torch.tensor([ms], device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    ms_per_step = ms / a.steps
+
+    # ---- end to end through the public API with HOST buffers: every step copies that step's input
+    #      field host->device (pinned) and reads the prediction back device->host.
+    field_host = torch.empty(N_local, fw).pin_memory()
+    field_host.copy_(eng.field0.cpu())
+    pred_host = torch.empty(N_local, nf).pin_memory()
+    e2e_steps = max(3, a.steps // 2)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for t in range(e2e_steps):
+        eng.node_in[:, :fw].copy_(field_host, non_blocking=True)
+        eng.step_only()
+        pred_host.copy_(eng.pred, non_blocking=True)
+        torch.cuda.current_stream().synchronize()        # the caller consumes pred on the host
+        field_host[:, fw - nf:] = pred_host               # host-side shift_and_replace (n_in = 1)
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    if world > 1:
+        tms = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        e2e_ms = float(tms.item())
+    e2e_val = e2e_steps / (e2e_ms * 1e-3)
+
+    # ---- roofline of the dominant kernel: the level-1 fused MP launch (edge output kept), timed alone with
+    #      CUDA events on the launching stream, inputs (3 GB of edge features) far larger than L2.
+    roof = None
+    if rank == 0:
+        roof = roofline_mp(eng, a, dev, ms_per_step)
+
+    if rank == 0:
+        cb = None
+        if not a.skip_cpu_baseline and world == 1:
+            cb, _ = cpu_steps_per_s(a, 2, 1, a.cpu_sample_nodes)
+        line = {"metric": "rollout_steps_per_s", "value": a.steps / (ms * 1e-3), "unit": "steps/s", "n_gpus": world,
+                "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32" if a.precision == "fp32" else a.precision,
+                "data": "synthetic",
+                "config": {"workload": workload_name(a), "precision": a.precision,
+                           "parallelism": f"node-range partition x{world}" if world > 1 else "single GPU",
+                           "cuda_graph": not a.no_graph, "weights": "seeded default init",
+                           "l2": "inputs larger than L2 (level-1 edge features %.1f GB per buffer)" % (a.nodes * a.k * a.hidden * 4 / 1e9)},
+                "clocks": clocks,
+                "e2e": {"value": e2e_val, "unit": "steps/s", "h2d_bytes_per_step": N_local * fw * 4 * world,
+                        "d2h_bytes_per_step": N_local * nf * 4 * world, "steps": e2e_steps},
+                "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cb}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def roofline_mp(eng, a, dev, ms_per_step):
+    from graphs4cfd_b200 import ops
+    mp_steps = [s for s in eng.steps if s[0] == "mp"]
+    lvl1 = [s for s in mp_steps if s[1]["topo"].n_edges == mp_steps[0][1]["topo"].n_edges]
+    arg = next(s[1] for s in lvl1 if s[1]["e_out"] is not None)
+    topo = arg["topo"]
+    H = a.hidden
+
+    def launch():
+        ops.mp(arg["ep"], arg["np_"], topo, arg["e_in"], arg["v_in"], arg["v_in"], act_e="selu", act_t="selu",
+               want_e=True, precision=eng.precision, e_out=arg["e_out"], t_out=arg["v_out"])
+
+    for _ in range(2):
+        launch()
+    torch.cuda.synchronize(dev)
+    reps = 5
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        launch()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    dur_ms = e0.elapsed_time(e1) / reps
+    E, N = topo.n_edges, topo.n_targets
+    alg_bytes = 4 * H * (2 * E + 2 * N) + 4 * E + (0 if topo.fixed_k else 4 * N)
+    flops = 2 * E * (3 * H * H + 2 * H * H) + 2 * N * (2 * H * H + 2 * H * H)
+    peaks, src = {}, "fallback"
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        src = "measured"
+    except Exception:
+        peaks = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
+    achieved = alg_bytes / (dur_ms * 1e-3) / 1e9
+    n_with_e = sum(1 for s in lvl1 if s[1]["e_out"] is not None)
+    return {"kernel": "mp_kernel (level-1 fused edge-MLP + aggregate + node-MLP)", "bound": "hbm",
+            "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+            "peak_source": src, "traffic": None, "launch_ms": dur_ms, "algorithmic_bytes": alg_bytes,
+            "algorithmic_tflop": flops / 1e12, "achieved_tflops": flops / (dur_ms * 1e-3) / 1e12,
+            "level1_launches_per_step": len(lvl1), "share_of_step": len(lvl1) * dur_ms / ms_per_step,
+            "note": f"{n_with_e} of {len(lvl1)} level-1 launches write e'; share uses this launch's duration for all"}
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_g4c(args)
