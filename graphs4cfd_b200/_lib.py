@@ -23,7 +23,8 @@ _i32p = C.c_void_p
 
 class Mlp(C.Structure):
     _fields_ = [("n_layers", C.c_int32), ("in_width", C.c_int32), ("hidden", C.c_int32), ("out_width", C.c_int32),
-                ("W_t", _f32p * MAX_LAYERS), ("b", _f32p * MAX_LAYERS), ("ln_gamma", _f32p), ("ln_beta", _f32p)]
+                ("W_t", _f32p * MAX_LAYERS), ("b", _f32p * MAX_LAYERS), ("ln_gamma", _f32p), ("ln_beta", _f32p),
+                ("W_pack", C.c_void_p * MAX_LAYERS), ("w_inv_scale", C.c_float * MAX_LAYERS), ("_pad", C.c_int32)]
 
 
 class Seg(C.Structure):
@@ -90,6 +91,7 @@ EXPORTS = {
     "g4c_halo_pack": (C.c_int, [C.POINTER(HaloDesc), C.c_void_p]),
     "g4c_halo_unpack": (C.c_int, [C.POINTER(HaloDesc), C.c_void_p]),
     "g4c_host_guillard": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
+    "g4c_debug_tc_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_int32, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

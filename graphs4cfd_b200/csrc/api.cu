@@ -37,6 +37,7 @@ int edge_to_node_launch(const G4cEdgeToNodeDesc& d, cudaStream_t st);
 int interp_launch(const G4cInterpDesc& d, cudaStream_t st);
 int step_update_launch(const G4cStepUpdateDesc& d, cudaStream_t st);
 int halo_launch(const G4cHaloDesc& d, cudaStream_t st, bool pack);
+int tc_gemm_test_launch(const float* A, const void* W_pack, float inv_scale, int K, float* D, cudaStream_t st);
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -150,6 +151,11 @@ int g4c_halo_pack(const G4cHaloDesc* d, void* stream) {
 int g4c_halo_unpack(const G4cHaloDesc* d, void* stream) {
     if (!d || !d->idx || !d->src || !d->dst || (d->width & 3)) { set_error("g4c_halo_unpack: bad descriptor"); return G4C_EINVAL; }
     return halo_launch(*d, static_cast<cudaStream_t>(stream), false);
+}
+
+int g4c_debug_tc_gemm(const float* A, const void* W_pack, float w_inv_scale, int32_t K, float* D, void* stream) {
+    if (!A || !W_pack || !D) { set_error("g4c_debug_tc_gemm: NULL pointer"); return G4C_EINVAL; }
+    return tc_gemm_test_launch(A, W_pack, w_inv_scale, K, D, static_cast<cudaStream_t>(stream));
 }
 
 int g4c_host_guillard(const int64_t* senders, int64_t n, int32_t k, uint8_t* coarse_mask) {

@@ -1,0 +1,161 @@
+// tc_core.cuh — Blackwell (sm_100a) primitives for the tensor-core path: mbarrier, bulk async copy
+// (TMA engine, 1-D), TMEM allocation, tcgen05.mma / commit / ld, UMMA descriptors, and the fp32 ->
+// (hi, lo) fp16 operand split written straight into the 128B-swizzled K-major shared-memory image
+// that tcgen05.mma reads.
+//
+// Operand image ("K-block"): 128 rows x 64 fp16 (128 B per row), rows packed at 128 B pitch, the eight
+// 16-byte chunks of row r stored at chunk position (c ^ (r & 7)).  This is the canonical
+// SWIZZLE_128B K-major layout: 8-row groups are 1024 B apart (descriptor SBO), the block base is
+// 1024-byte aligned, and stepping K by 16 elements inside the block advances the descriptor start
+// address by 32 bytes.
+#pragma once
+#include <cuda_fp16.h>
+#include "common.cuh"
+
+namespace g4c {
+namespace tc {
+
+constexpr int kBlockBytes = 128 * 128;          // one K-block image: 128 rows x 128 B
+constexpr uint32_t kIdescF16_M128_N128 =        // kind::f16: D=f32, A=B=f16, K-major both, N=128, M=128
+    (1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// ------------------------------------------------------------------ mbarrier
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) { }
+}
+
+// ------------------------------------------------------------------ async (TMA engine) bulk copy, 1-D
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// generic-proxy writes (st.shared) -> visible to the async proxy (tcgen05.mma operand reads)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ------------------------------------------------------------------ TMEM
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_holder, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_holder)), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// ------------------------------------------------------------------ UMMA
+// shared-memory matrix descriptor, K-major, SWIZZLE_128B, 8-row group pitch 1024 B, version 1 (sm_100)
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);          // start address      [0,14)
+    d |= (uint64_t)(16 >> 4) << 16;                       // leading byte offset (unused for SW128 K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                     // stride byte offset  [32,46)
+    d |= (uint64_t)1 << 46;                               // descriptor version  [46,48)
+    d |= (uint64_t)2 << 61;                               // layout: SWIZZLE_128B
+    return d;
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, one 128x128x16 fp16 MMA issued by the calling thread
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on `bar` when every previously issued tcgen05.mma of this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// 32 consecutive fp32 columns of this thread's TMEM lane (warp w reads lanes 32*(w%4) .. +31)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ------------------------------------------------------------------ operand split
+// x = hi + lo with hi = fp16(x), lo = fp16(x - hi): 22 significant bits between the two halves.
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// byte offset of element (row r, k) inside an operand made of consecutive K-blocks
+__device__ __forceinline__ uint32_t sw128_offset(int r, int k) {
+    const int kb = k >> 6, kk = k & 63;
+    return (uint32_t)kb * kBlockBytes + (uint32_t)r * 128 + (uint32_t)(((kk >> 3) ^ (r & 7)) << 4) + (uint32_t)((kk & 7) << 1);
+}
+
+// store 8 consecutive k (k0 % 8 == 0) of row r: one 16-byte chunk each into the hi and lo images
+__device__ __forceinline__ void store_split8(uint8_t* hi_img, uint8_t* lo_img, int r, int k0, const float (&x)[8]) {
+    uint4 h, l;
+    split2(x[0], x[1], h.x, l.x);
+    split2(x[2], x[3], h.y, l.y);
+    split2(x[4], x[5], h.z, l.z);
+    split2(x[6], x[7], h.w, l.w);
+    const uint32_t off = sw128_offset(r, k0);
+    *reinterpret_cast<uint4*>(hi_img + off) = h;
+    *reinterpret_cast<uint4*>(lo_img + off) = l;
+}
+
+// Issue the 3-term split product for one K-block (64 k): D += Ah*Wh + Al*Wh + Ah*Wl  (12 MMAs).
+// a_hi/a_lo/w_hi/w_lo are shared-memory byte addresses of the K-block images.
+__device__ __forceinline__ void issue_kblock_x3(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t w_hi, uint32_t w_lo,
+                                                bool first) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint64_t ah = make_desc_sw128(a_hi + j * 32), al = make_desc_sw128(a_lo + j * 32);
+        const uint64_t wh = make_desc_sw128(w_hi + j * 32), wl = make_desc_sw128(w_lo + j * 32);
+        umma_f16(d_tmem, ah, wh, kIdescF16_M128_N128, (first && j == 0) ? 0u : 1u);
+        umma_f16(d_tmem, al, wh, kIdescF16_M128_N128, 1u);
+        umma_f16(d_tmem, ah, wl, kIdescF16_M128_N128, 1u);
+    }
+}
+
+}  // namespace tc
+}  // namespace g4c

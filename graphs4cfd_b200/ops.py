@@ -1,11 +1,39 @@
 """Tensor-level wrappers over the C ABI (include/g4c.h): PyTorch tensors in, PyTorch tensors out.
 PyTorch only owns the memory and the stream; every computation below is a libg4c kernel."""
 import ctypes as C
+import math
 from typing import List, Optional, Sequence, Tuple
 
 import torch
 
 from . import _lib as L
+
+
+def pack_weight_fp16x2(W: torch.Tensor):
+    """Tensor-core operand image of one nn.Linear weight W [128, K] (torch layout, K % 64 == 0):
+    s*W = hi + lo in fp16 (s a power of two keeping |s*W| in [512, 1024) so the residual stays a normal
+    fp16), each 64-wide K-block stored as a 128-row x 128-byte SWIZZLE_128B K-major image, hi image then
+    lo image (32 KiB per K-block).  Returns (uint8 tensor, 1/s)."""
+    N, K = W.shape
+    assert N == 128 and K % 64 == 0, "tensor-core path: weights must be [128, 64*j]"
+    W = W.detach().float()
+    amax = float(W.abs().max())
+    s = 1.0 if amax == 0.0 else 2.0 ** min(14, math.floor(math.log2(1000.0 / amax)))
+    Ws = W * s
+    hi = Ws.half()
+    lo = (Ws - hi.float()).half()
+    r = torch.arange(128, device=W.device)
+    c = torch.arange(8, device=W.device)
+    phys = c.unsqueeze(0) ^ (r.unsqueeze(1) & 7)                       # [128, 8]: position of logical chunk c in row r
+
+    def image(M):
+        blk = M.view(128, K // 64, 8, 8).permute(1, 0, 2, 3)            # [kb, row, chunk, 8]
+        out = torch.empty_like(blk)
+        out[:, r.unsqueeze(1), phys, :] = blk
+        return out.reshape(K // 64, 1, 128, 64)
+
+    pack = torch.cat([image(hi), image(lo)], dim=1).contiguous()        # [kb, hi|lo, 128, 64] fp16
+    return pack.view(torch.uint8).reshape(-1), 1.0 / s
 
 
 class MlpPack:
@@ -32,6 +60,13 @@ class MlpPack:
                                            ln[1].detach().float().contiguous().clone())
         L.require_cuda_f32(*self.W_t, *self.b)
         self._struct = None
+        # tensor-core images (hidden = 128 only; the first layer's K must be a multiple of 64)
+        self.W_pack, self.w_inv_scale = [], []
+        if self.hidden == 128 and self.out_width == 128 and self.in_width % 64 == 0:
+            for W, _ in linears:
+                pk, inv = pack_weight_fp16x2(W)
+                self.W_pack.append(pk)
+                self.w_inv_scale.append(inv)
 
     @classmethod
     def from_module(cls, mlp_module):
@@ -64,6 +99,9 @@ class MlpPack:
                 m.b[i] = self.b[i].data_ptr()
             if self.ln is not None:
                 m.ln_gamma, m.ln_beta = self.ln[0].data_ptr(), self.ln[1].data_ptr()
+            for i, pk in enumerate(self.W_pack):
+                m.W_pack[i] = pk.data_ptr()
+                m.w_inv_scale[i] = self.w_inv_scale[i]
             self._struct = m
         return self._struct
 
@@ -227,3 +265,12 @@ def halo_unpack(buf, idx, dst):
     d.idx, d.src, d.dst = idx.data_ptr(), buf.data_ptr(), dst.data_ptr()
     L.check(L.lib().g4c_halo_unpack(C.byref(d), L.stream_ptr()))
     return dst
+
+
+def debug_tc_gemm(A: torch.Tensor, W: torch.Tensor) -> torch.Tensor:
+    """A[128,K] @ W[128,K]^T through the tensor-core GEMM core (self test)."""
+    L.require_cuda_f32(A, W)
+    pk, inv = pack_weight_fp16x2(W)
+    D = torch.empty(128, 128, device=A.device, dtype=torch.float32)
+    L.check(L.lib().g4c_debug_tc_gemm(A.data_ptr(), pk.data_ptr(), inv, int(A.shape[1]), D.data_ptr(), L.stream_ptr()))
+    return D

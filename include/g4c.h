@@ -54,6 +54,13 @@ typedef struct {
     const float* b[G4C_MAX_LAYERS];
     const float* ln_gamma;            /* NULL = no layer_norm                                 */
     const float* ln_beta;
+    /* tensor-core operand images (G4C_PREC_FP16X3), NULL when only the fp32 path is used:
+     * layer l = in_l/64 stages of 32 KiB; stage kb = fp16(s*W)[:, 64kb:64kb+64] as a 128-row x 128 B
+     * SWIZZLE_128B K-major image (16 KiB) followed by the same image of the residual
+     * fp16(s*W - hi) (16 KiB); w_inv_scale[l] = 1/s, s a power of two. */
+    const void* W_pack[G4C_MAX_LAYERS];
+    float w_inv_scale[G4C_MAX_LAYERS];
+    int32_t _pad;
 } G4cMlp;
 
 /* One input segment of a concatenation `torch.cat((seg0, seg1, ...), dim=-1)`. */
@@ -214,6 +221,10 @@ G4C_API int64_t g4c_launch_count(void);
 
 /* host-side plan helper (HOST pointers): Guillard node-nested coarsening, the sequential sweep of
  * transforms/mugs.py:8-29.  senders = int64 [n, k]; coarse_mask = uint8 [n] (out). */
+/* self-test of the tensor-core GEMM core: D[128,128] = A[128,K] * W^T with the 3-term fp16 split,
+ * W given as a W_pack image (K % 64 == 0, K <= 128).  Used by tests/test_gpu_tc.py. */
+G4C_API int g4c_debug_tc_gemm(const float* A, const void* W_pack, float w_inv_scale, int32_t K, float* D, void* stream);
+
 G4C_API int g4c_host_guillard(const int64_t* senders, int64_t n, int32_t k, uint8_t* coarse_mask);
 
 #ifdef __cplusplus
