@@ -203,7 +203,7 @@ class Rollout:
                 ops.rowmlp(a["pack"], a["segs"], rows=a.get("rows"), act=a["act"], out=a["out"], residual=a.get("residual"))
             elif op == "mp":
                 ops.mp(a["ep"], a["np_"], a["topo"], a["e_in"], a.get("s_in", a["v_in"]), a["v_in"],
-                       aggr=a.get("aggr", "mean"), act_e="selu", act_t="selu",
+                       aggr=a.get("aggr", "mean"), act_e=a.get("act_e", "selu"), act_t=a.get("act_t", "selu"),
                        want_e=a["e_out"] is not None, precision=self.precision, e_out=a["e_out"], t_out=a["v_out"])
             elif op == "seg":
                 ops.seg_reduce(a["x"], a["ptr"], a["idx"], a["n"], "mean", a["act"], out=a["out"])
