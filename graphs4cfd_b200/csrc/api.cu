@@ -38,6 +38,7 @@ int interp_launch(const G4cInterpDesc& d, cudaStream_t st);
 int step_update_launch(const G4cStepUpdateDesc& d, cudaStream_t st);
 int halo_launch(const G4cHaloDesc& d, cudaStream_t st, bool pack);
 int tc_gemm_test_launch(const float* A, const void* W_pack, float inv_scale, int K, float* D, cudaStream_t st);
+int tc2_test_launch(int test, const float* A, const void* Wpack, float inv_scale, const float* P, float* D, int flags, cudaStream_t st);
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -156,6 +157,11 @@ int g4c_halo_unpack(const G4cHaloDesc* d, void* stream) {
 int g4c_debug_tc_gemm(const float* A, const void* W_pack, float w_inv_scale, int32_t K, float* D, void* stream) {
     if (!A || !W_pack || !D) { set_error("g4c_debug_tc_gemm: NULL pointer"); return G4C_EINVAL; }
     return tc_gemm_test_launch(A, W_pack, w_inv_scale, K, D, static_cast<cudaStream_t>(stream));
+}
+
+int g4c_debug_tc2(int32_t test, const float* A, const void* W_pack, float w_inv_scale, const float* P, float* D, int32_t flags, void* stream) {
+    if (!A || !W_pack || !D || (test == 2 && !P)) { set_error("g4c_debug_tc2: NULL pointer"); return G4C_EINVAL; }
+    return tc2_test_launch(test, A, W_pack, w_inv_scale, P, D, flags, static_cast<cudaStream_t>(stream));
 }
 
 int g4c_host_guillard(const int64_t* senders, int64_t n, int32_t k, uint8_t* coarse_mask) {

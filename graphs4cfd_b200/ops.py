@@ -36,6 +36,43 @@ def pack_weight_fp16x2(W: torch.Tensor):
     return pack.view(torch.uint8).reshape(-1), 1.0 / s
 
 
+def _swizzled_images(M: torch.Tensor):
+    """fp16 [R, K] (R % 8 == 0, K % 64 == 0) -> [K/64, R, 64] fp16, each a SWIZZLE_128B K-major image."""
+    R, K = M.shape
+    r = torch.arange(R, device=M.device)
+    c = torch.arange(8, device=M.device)
+    phys = c.unsqueeze(0) ^ (r.unsqueeze(1) & 7)
+    blk = M.view(R, K // 64, 8, 8).permute(1, 0, 2, 3)
+    out = torch.empty_like(blk)
+    out[:, r.unsqueeze(1), phys, :] = blk
+    return out.reshape(K // 64, R, 64)
+
+
+def weight_scale(W: torch.Tensor) -> float:
+    """Power-of-two s keeping |s*W| below 1024 so the fp16 residual of s*W stays a normal number."""
+    amax = float(W.abs().max())
+    return 1.0 if amax == 0.0 else 2.0 ** min(14, math.floor(math.log2(1000.0 / amax)))
+
+
+def pack_weight_pair(W: torch.Tensor, s: Optional[float] = None):
+    """Operand images of W [128, K] for a CTA pair (cta_group::2): CTA r holds output rows [64r, 64r+64).
+    Layout [r][kb][hi|lo][64 rows][64 fp16] (8 KiB images).  Returns (uint8 tensor, 1/s)."""
+    N, K = W.shape
+    assert N == 128 and K % 64 == 0
+    W = W.detach().float()
+    s = weight_scale(W) if s is None else s
+    Ws = W * s
+    hi = Ws.half()
+    lo = (Ws - hi.float()).half()
+    parts = []
+    for r in range(2):
+        h = _swizzled_images(hi[64 * r:64 * r + 64].contiguous())      # [kb, 64, 64]
+        l = _swizzled_images(lo[64 * r:64 * r + 64].contiguous())
+        parts.append(torch.stack([h, l], dim=1))                        # [kb, 2, 64, 64]
+    pack = torch.stack(parts, dim=0).contiguous()                       # [2, kb, 2, 64, 64]
+    return pack.view(torch.uint8).reshape(-1), 1.0 / s
+
+
 class MlpPack:
     """Device-resident weights of one reference ``MLP`` (graphs4cfd/nn/blocks.py:129-144) in the
     layout the kernels read: every Linear transposed to [in, out] (a final layer narrower than 16
@@ -265,6 +302,16 @@ def halo_unpack(buf, idx, dst):
     d.idx, d.src, d.dst = idx.data_ptr(), buf.data_ptr(), dst.data_ptr()
     L.check(L.lib().g4c_halo_unpack(C.byref(d), L.stream_ptr()))
     return dst
+
+
+def debug_tc2(test: int, A: torch.Tensor, W: torch.Tensor, P: Optional[torch.Tensor] = None, flags: int = 0) -> torch.Tensor:
+    """Self tests of the TMEM-operand / tcgen05.cp / CTA-pair primitives (csrc/tc2_test.cu)."""
+    L.require_cuda_f32(A, W, P)
+    pk, inv = pack_weight_pair(W) if test == 3 else pack_weight_fp16x2(W)
+    D = torch.zeros(A.shape[0], 128, device=A.device, dtype=torch.float32)
+    L.check(L.lib().g4c_debug_tc2(test, A.data_ptr(), pk.data_ptr(), inv, 0 if P is None else P.data_ptr(),
+                                  D.data_ptr(), flags, L.stream_ptr()))
+    return D
 
 
 def debug_tc_gemm(A: torch.Tensor, W: torch.Tensor) -> torch.Tensor:

@@ -225,6 +225,11 @@ G4C_API int64_t g4c_launch_count(void);
  * W given as a W_pack image (K % 64 == 0, K <= 128).  Used by tests/test_gpu_tc.py. */
 G4C_API int g4c_debug_tc_gemm(const float* A, const void* W_pack, float w_inv_scale, int32_t K, float* D, void* stream);
 
+/* self tests of the second-generation primitives (A operand in TMEM, tcgen05.cp, CTA pairs); see
+ * graphs4cfd_b200/csrc/tc2_test.cu for the meaning of test / flags.  Used by tests/test_gpu_tc2.py. */
+G4C_API int g4c_debug_tc2(int32_t test, const float* A, const void* W_pack, float w_inv_scale, const float* P, float* D,
+                          int32_t flags, void* stream);
+
 G4C_API int g4c_host_guillard(const int64_t* senders, int64_t n, int32_t k, uint8_t* coarse_mask);
 
 #ifdef __cplusplus
