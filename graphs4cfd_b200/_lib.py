@@ -46,6 +46,14 @@ class MpDesc(C.Structure):
                 ("edge_mlp", Mlp), ("node_mlp", Mlp)]
 
 
+class EdgeDesc(C.Structure):
+    _fields_ = [("n_targets", C.c_int64), ("n_edges", C.c_int64), ("fixed_k", C.c_int32), ("n_layers", C.c_int32),
+                ("act_e_out", C.c_int32), ("aggr", C.c_int32), ("rowptr", _i32p), ("src", _i32p), ("edge_perm", _i32p),
+                ("tgt_perm", _i32p), ("e_in", _f32p), ("P_r", _f32p), ("P_c", _f32p), ("e_out", _f32p),
+                ("agg_out", _f32p), ("W", C.c_void_p * 3), ("inv_scale", C.c_float * 3), ("p_scale", C.c_float),
+                ("bias", _f32p * 3), ("gamma", _f32p), ("beta", _f32p)]
+
+
 class SegReduceDesc(C.Structure):
     _fields_ = [("n_groups", C.c_int64), ("width", C.c_int32), ("aggr", C.c_int32), ("act_out", C.c_int32),
                 ("_pad", C.c_int32), ("ptr", _i32p), ("idx", _i32p), ("x", _f32p), ("out", _f32p)]
@@ -83,6 +91,7 @@ EXPORTS = {
     "g4c_launch_count": (C.c_int64, []),
     "g4c_rowmlp_fwd": (C.c_int, [C.POINTER(RowMlpDesc), C.c_void_p]),
     "g4c_mp_fwd": (C.c_int, [C.POINTER(MpDesc), C.c_void_p]),
+    "g4c_edge_aggr_fwd": (C.c_int, [C.POINTER(EdgeDesc), C.c_void_p]),
     "g4c_seg_reduce_fwd": (C.c_int, [C.POINTER(SegReduceDesc), C.c_void_p]),
     "g4c_project_fwd": (C.c_int, [C.POINTER(ProjectDesc), C.c_void_p]),
     "g4c_edge_to_node_fwd": (C.c_int, [C.POINTER(EdgeToNodeDesc), C.c_void_p]),

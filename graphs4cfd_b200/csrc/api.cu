@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include "common.cuh"
+#include "mp_pair.h"
 
 namespace g4c {
 
@@ -112,6 +113,25 @@ int g4c_mp_fwd(const G4cMpDesc* d, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (d->precision == G4C_PREC_FP32) return mp_fp32_dispatch(*d, st);
     return mp_tc_dispatch(*d, st);
+}
+
+int g4c_edge_aggr_fwd(const G4cEdgeDesc* d, void* stream) {
+    if (!d) { set_error("g4c_edge_aggr_fwd: NULL descriptor"); return G4C_EINVAL; }
+    if (d->n_targets < 0 || d->n_edges < 0 || d->n_edges > 0x7fffffffLL || d->n_targets > 0x7fffffffLL) { set_error("g4c_edge_aggr_fwd: bad sizes"); return G4C_EINVAL; }
+    if (d->n_layers < 2 || d->n_layers > 3) { set_error("g4c_edge_aggr_fwd: n_layers=%d (2..3)", d->n_layers); return G4C_EUNSUPPORTED; }
+    if (d->fixed_k < 0 || (d->fixed_k == 0 && !d->rowptr)) { set_error("g4c_edge_aggr_fwd: need fixed_k > 0 or rowptr"); return G4C_EINVAL; }
+    if (d->fixed_k > 0 && d->n_edges != d->n_targets * d->fixed_k) { set_error("g4c_edge_aggr_fwd: n_edges != n_targets*fixed_k"); return G4C_EINVAL; }
+    if (!d->agg_out || !d->P_c || (d->n_edges > 0 && (!d->src || !d->e_in || !d->P_r))) { set_error("g4c_edge_aggr_fwd: NULL tensor"); return G4C_EINVAL; }
+    if (!aligned16(d->e_in) || !aligned16(d->P_r) || !aligned16(d->P_c) || ((reinterpret_cast<uintptr_t>(d->e_out) | reinterpret_cast<uintptr_t>(d->agg_out)) & 31)) {
+        set_error("g4c_edge_aggr_fwd: inputs must be 16-byte, outputs 32-byte aligned"); return G4C_EINVAL; }
+    if (d->e_out && d->e_out == d->e_in) { set_error("g4c_edge_aggr_fwd: e_out must not alias e_in"); return G4C_EINVAL; }
+    for (int l = 0; l < d->n_layers; ++l) {
+        if (!d->W[l] || !aligned16(d->W[l]) || (l > 0 && !d->bias[l])) { set_error("g4c_edge_aggr_fwd: bad weights at layer %d", l + 1); return G4C_EINVAL; }
+    }
+    if ((d->gamma == nullptr) != (d->beta == nullptr)) { set_error("g4c_edge_aggr_fwd: gamma/beta must both be set or NULL"); return G4C_EINVAL; }
+    if (d->aggr != G4C_AGGR_MEAN && d->aggr != G4C_AGGR_SUM) { set_error("g4c_edge_aggr_fwd: aggr=%d", d->aggr); return G4C_EINVAL; }
+    if (d->n_targets == 0) return G4C_OK;
+    return edge_pair_launch(*d, static_cast<cudaStream_t>(stream));
 }
 
 int g4c_seg_reduce_fwd(const G4cSegReduceDesc* d, void* stream) {

@@ -20,6 +20,20 @@ __device__ __forceinline__ float apply_act(float x, int act) {
     return x;
 }
 
+// branch-free SELU on the SFU: exp(x) = ex2.approx(x*log2(e)) (2 ulp); absolute error of the negative branch
+// ~2e-7, the same order as the cancellation in the reference's fp32 `exp(x) - 1`.
+__device__ __forceinline__ float selu_fast(float x) {
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 1.4426950408889634f));
+    const float neg = fmaf(kSeluScale * kSeluAlpha, e, -(kSeluScale * kSeluAlpha));
+    return x > 0.f ? kSeluScale * x : neg;
+}
+__device__ __forceinline__ float apply_act_fast(float x, int act) {
+    if (act == G4C_ACT_SELU) return selu_fast(x);
+    if (act == G4C_ACT_TANH) return tanhf(x);
+    return x;
+}
+
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));

@@ -1,0 +1,417 @@
+// mp_edge_pair.cu — fused edge-MLP + aggregation kernel of the message-passing block, hidden = 128,
+// on CTA pairs (cta_group::2) with every operand that is re-used kept on chip.
+//
+// Reference arithmetic (graphs4cfd/nn/blocks.py:181-183, 328-330, 376-378):
+//     e' = LN(MLP(cat(e, S[src], T[tgt]))) ;  agg[t] = mean/sum over the in-edges of t of e'
+// The first Linear is split exactly:  W1 [e, S[src], T[tgt]] + b1 = W1e e + P_r[src] + P_c[tgt]  with
+// P_r = S W1s^T and P_c = T W1t^T + b1 computed once per NODE by the row kernel (mp_row_pair.cu), so the
+// per-edge GEMMs are all K = 128 and the [E,3H] concatenation never exists.
+//
+// Work decomposition: a CTA pair owns two consecutive units of 128 targets (one per CTA).  Slot j of a
+// unit is the tile made of the j-th in-edge of each of its 128 targets, so tile row m always belongs to
+// target m: TMEM lane m / accumulator row m, and the aggregation is a register accumulation in the
+// epilogue thread that owns the row (fixed order, no atomics).
+//
+// Per CTA (512 threads):
+//   warps 0-7   epilogue: thread (row, half) owns 64 columns of its row.  TMEM -> registers, bias, SELU,
+//               fp16 (hi, lo) split written back to TMEM as the next layer's A operand (tcgen05.st); last
+//               layer: LayerNorm, aggregation, activation, 256-bit stores of e'.
+//   warps 8-11  loaders: coalesced 512-byte row reads of e, P_r[src], P_c[tgt]; e is split into fp16 (hi, lo)
+//               operand images, P_r + P_c (pre-scaled) into fp32 images; tcgen05.cp then moves the images
+//               into TMEM (A operand / initial accumulator), transposing "warp reads a row" into "lane owns
+//               a row" in hardware.
+//   warp 12     (leader CTA) issues every tcgen05.cp / tcgen05.mma of the pair; M = 256, N = 128, the B
+//               operand (weights) is resident in shared memory, each CTA holding 64 of the 128 output rows
+//               of all layers as pre-split, pre-swizzled fp16 (hi, lo) images (96 KiB).
+// Two chains (even / odd slots) alternate so that the MMAs of one overlap the epilogue of the other.
+// TMEM: chain c uses columns [256c, 256c+128) accumulator, [256c+128, +64) A hi, [256c+192, +64) A lo.
+#include <algorithm>
+#include "tc2_core.cuh"
+#include "mp_pair.h"
+
+namespace g4c {
+namespace ep {
+
+using namespace tc2;
+
+constexpr int H = 128;
+constexpr int IMG = 128 * 128;
+constexpr int HIMG = 64 * 128;
+constexpr int NT = 512;
+constexpr int NEPI = 256;
+constexpr int kRegsEpi = 200, kRegsLoad = 72, kRegsMisc = 40;
+
+struct Smem {
+    uint8_t w[3][4 * HIMG];          // layer l: K-block 0 hi | lo, K-block 1 hi | lo (64-row images)
+    uint8_t img_e[4][IMG];           // hi k0..63, hi k64..127, lo k0..63, lo k64..127
+    uint8_t img_p[4][IMG];           // fp32 columns 32q .. 32q+31
+    float part[2][2][128];           // LayerNorm partial sums [pass][half][row]
+    uint64_t w_full;
+    uint64_t in_full, in_empty;      // in_full: leader, 8 loader warps of the pair; in_empty: local, multicast commit
+    uint64_t a_ready[2], d_free[2];  // leader, 16 epilogue warps of the pair
+    uint64_t d_full[2];              // local, multicast commit
+    uint32_t tmem_base;
+};
+
+static_assert(sizeof(Smem) <= 232448, "edge kernel shared memory exceeds the 227 KiB opt-in limit");
+
+__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory"); }
+
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
+__device__ __forceinline__ void stg256(float* p, const float* v) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
+                 "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+                 : "memory");
+}
+
+// largest in-degree over the (up to) 256 targets of unit pair `up`; executed by a full warp
+__device__ __forceinline__ int pair_maxdeg(const EdgeArgs& a, int64_t up, int lane) {
+    if (a.fixed_k > 0) return a.fixed_k;
+    int m = 0;
+    const int64_t n0 = up * 256;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int64_t n = n0 + i * 32 + lane;
+        if (n < a.n_targets) m = max(m, a.rowptr[n + 1] - a.rowptr[n]);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, off));
+    return m;
+}
+
+struct RowMeta {
+    int deg, base, trow;             // trow < 0: no such target
+};
+__device__ __forceinline__ RowMeta row_meta(const EdgeArgs& a, int64_t n) {
+    RowMeta r{0, 0, -1};
+    if (n < a.n_targets) {
+        if (a.fixed_k > 0) { r.base = (int)(n * a.fixed_k); r.deg = a.fixed_k; }
+        else { r.base = a.rowptr[n]; r.deg = a.rowptr[n + 1] - r.base; }
+        r.trow = a.tgt_perm ? a.tgt_perm[n] : (int)n;
+    }
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------- epilogues
+// hidden layer: x = selu(acc*inv (+ bias)); written as fp16 (hi, lo) A operand columns of this thread's row
+__device__ __forceinline__ void epilogue_hidden(uint32_t d_addr, uint32_t ah_addr, uint32_t al_addr, float inv,
+                                                const float* __restrict__ bias) {
+#pragma unroll
+    for (int c0 = 0; c0 < 64; c0 += 32) {
+        float v[32];
+        tmem_ld32f(d_addr + c0, v);
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (bias) b = __ldg(reinterpret_cast<const float4*>(bias + c0 + i));
+            const float x0 = selu_fast(fmaf(v[i], inv, b.x)), x1 = selu_fast(fmaf(v[i + 1], inv, b.y));
+            const float x2 = selu_fast(fmaf(v[i + 2], inv, b.z)), x3 = selu_fast(fmaf(v[i + 3], inv, b.w));
+            split2(x0, x1, hi[i / 2], lo[i / 2]);
+            split2(x2, x3, hi[i / 2 + 1], lo[i / 2 + 1]);
+        }
+        tmem_st16(ah_addr + c0 / 2, hi);
+        tmem_st16(al_addr + c0 / 2, lo);
+    }
+    tmem_wait_st();
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_pair_kernel(const EdgeArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    Smem& s = *reinterpret_cast<Smem*>(smem_raw);
+    if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int nl = a.n_layers;
+    const int64_t n_units = (a.n_targets + 127) / 128;
+    const int64_t n_up = (n_units + 1) / 2;
+    const int64_t up0 = blockIdx.x >> 1, up_stride = gridDim.x >> 1;
+
+    if (tid == 0) {
+        mbar_init(&s.w_full, 1);
+        mbar_init(&s.in_full, 8);
+        mbar_init(&s.in_empty, 1);
+        for (int c = 0; c < 2; ++c) {
+            mbar_init(&s.a_ready[c], 16);
+            mbar_init(&s.d_free[c], 16);
+            mbar_init(&s.d_full[c], 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 12) { tmem_alloc<2>(&s.tmem_base, 512); tmem_relinquish<2>(); }
+    if (tid == 0) {
+        mbar_arrive_expect_tx(&s.w_full, (uint32_t)nl * 4 * HIMG);
+        for (int l = 0; l < nl; ++l) bulk_g2s(s.w[l], a.W[l] + (size_t)rank * 4 * HIMG, 4 * HIMG, &s.w_full);
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem = s.tmem_base;
+    const uint32_t leader_in_full = mapa(smem_u32(&s.in_full), 0);
+
+    if (warp < 8) {
+        // ====================================================================== epilogue warps
+        setmaxnreg_inc<kRegsEpi>();
+        const int row = (warp & 3) * 32 + lane, half = warp >> 2;
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        const uint32_t leader_a_ready[2] = {mapa(smem_u32(&s.a_ready[0]), 0), mapa(smem_u32(&s.a_ready[1]), 0)};
+        const uint32_t leader_d_free[2] = {mapa(smem_u32(&s.d_free[0]), 0), mapa(smem_u32(&s.d_free[1]), 0)};
+        uint32_t n_dfull[2] = {0, 0};
+        const float* gamma = a.gamma ? a.gamma + half * 64 : nullptr;
+        const float* beta = a.beta ? a.beta + half * 64 : nullptr;
+
+        for (int64_t up = up0; up < n_up; up += up_stride) {
+            const int maxdeg = pair_maxdeg(a, up, lane);
+            const RowMeta rm = row_meta(a, (up * 2 + rank) * 128 + row);
+            float agg[64];
+#pragma unroll
+            for (int i = 0; i < 64; ++i) agg[i] = 0.f;
+
+            for (int j0 = 0; j0 < maxdeg; j0 += 2) {
+                const int nch = min(2, maxdeg - j0);
+                for (int l = 0; l < nl; ++l) {
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        if (c >= nch) continue;
+                        const uint32_t d_addr = tmem + lane_base + 256u * c + 64u * half;
+                        mbar_wait(&s.d_full[c], n_dfull[c] & 1);
+                        ++n_dfull[c];
+                        tc_fence_after();
+                        if (l < nl - 1) {
+                            epilogue_hidden(d_addr, tmem + lane_base + 256u * c + 128u + 32u * half,
+                                            tmem + lane_base + 256u * c + 192u + 32u * half, a.inv_scale[l],
+                                            l == 0 ? nullptr : a.bias[l] + half * 64);
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive_cluster(leader_a_ready[c]);
+                        } else {
+                            // ---- last layer: LayerNorm, aggregation, store
+                            float y[64];
+                            const float inv = a.inv_scale[l];
+                            const float* bias = (l == 0) ? nullptr : a.bias[l] + half * 64;
+                            tmem_ld32f(d_addr, y);
+                            tmem_ld32f(d_addr + 32, y + 32);
+#pragma unroll
+                            for (int i = 0; i < 64; i += 4) {
+                                float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (bias) b = __ldg(reinterpret_cast<const float4*>(bias + i));
+                                y[i] = fmaf(y[i], inv, b.x);
+                                y[i + 1] = fmaf(y[i + 1], inv, b.y);
+                                y[i + 2] = fmaf(y[i + 2], inv, b.z);
+                                y[i + 3] = fmaf(y[i + 3], inv, b.w);
+                            }
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive_cluster(leader_d_free[c]);
+                            if (gamma) {
+                                float sum = 0.f;
+#pragma unroll
+                                for (int i = 0; i < 64; ++i) sum += y[i];
+                                s.part[0][half][row] = sum;
+                                epi_sync();
+                                const float mean = (s.part[0][0][row] + s.part[0][1][row]) * (1.f / H);
+                                float sq = 0.f;
+#pragma unroll
+                                for (int i = 0; i < 64; ++i) {
+                                    y[i] -= mean;
+                                    sq = fmaf(y[i], y[i], sq);
+                                }
+                                s.part[1][half][row] = sq;
+                                epi_sync();
+                                const float rstd = 1.f / sqrtf((s.part[1][0][row] + s.part[1][1][row]) * (1.f / H) + kLnEps);
+#pragma unroll
+                                for (int i = 0; i < 64; i += 4) {
+                                    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + i));
+                                    const float4 b = __ldg(reinterpret_cast<const float4*>(beta + i));
+                                    y[i] = fmaf(y[i] * rstd, g.x, b.x);
+                                    y[i + 1] = fmaf(y[i + 1] * rstd, g.y, b.y);
+                                    y[i + 2] = fmaf(y[i + 2] * rstd, g.z, b.z);
+                                    y[i + 3] = fmaf(y[i + 3] * rstd, g.w, b.w);
+                                }
+                            }
+                            const int j = j0 + c;
+                            if (rm.trow >= 0 && j < rm.deg) {
+#pragma unroll
+                                for (int i = 0; i < 64; ++i) agg[i] += y[i];
+                                if (a.e_out) {
+                                    const int slot = rm.base + j;
+                                    const int erow = a.edge_perm ? a.edge_perm[slot] : slot;
+                                    float* dst = a.e_out + (size_t)erow * H + half * 64;
+#pragma unroll
+                                    for (int i = 0; i < 64; i += 8) {
+                                        float o[8];
+#pragma unroll
+                                        for (int u = 0; u < 8; ++u) o[u] = apply_act_fast(y[i + u], a.act_e_out);
+                                        stg256(dst + i, o);
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            // ---- aggregated messages of this unit
+            if (rm.trow >= 0) {
+                const float cnt = (a.aggr == G4C_AGGR_MEAN) ? (float)max(rm.deg, 1) : 1.f;
+                float* dst = a.agg_out + (size_t)rm.trow * H + half * 64;
+#pragma unroll
+                for (int i = 0; i < 64; i += 8) {
+                    float o[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) o[u] = agg[i + u] / cnt;
+                    stg256(dst + i, o);
+                }
+            }
+        }
+    } else if (warp < 12) {
+        // ====================================================================== loader warps
+        setmaxnreg_dec<kRegsLoad>();
+        const int lw = warp - 8;
+        const float ps = a.p_scale;
+        uint32_t g = 0;
+        mbar_wait(&s.w_full, 0);           // in_full is only signalled once this CTA's weights have landed
+        for (int64_t up = up0; up < n_up; up += up_stride) {
+            const int maxdeg = pair_maxdeg(a, up, lane);
+            const RowMeta rm = row_meta(a, (up * 2 + rank) * 128 + lw * 32 + lane);
+            for (int j = 0; j < maxdeg; ++j, ++g) {
+                int erow = -1, srow = -1;
+                if (rm.trow >= 0 && j < rm.deg) {
+                    const int slot = rm.base + j;
+                    erow = a.edge_perm ? a.edge_perm[slot] : slot;
+                    srow = a.src[slot];
+                }
+                mbar_wait(&s.in_empty, (g + 1) & 1);
+#pragma unroll 1
+                for (int i0 = 0; i0 < 32; i0 += 4) {
+                    float4 xe[4], xr[4], xc[4];
+                    int er[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        er[u] = __shfl_sync(0xffffffffu, erow, i0 + u);
+                        const int sr = __shfl_sync(0xffffffffu, srow, i0 + u);
+                        const int tr = __shfl_sync(0xffffffffu, rm.trow, i0 + u);
+                        xe[u] = xr[u] = xc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (er[u] >= 0) {
+                            xe[u] = ldg_stream(a.e_in + (size_t)er[u] * H + lane * 4);
+                            xr[u] = __ldg(reinterpret_cast<const float4*>(a.P_r + (size_t)sr * H + lane * 4));
+                            xc[u] = __ldg(reinterpret_cast<const float4*>(a.P_c + (size_t)tr * H + lane * 4));
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int r = lw * 32 + i0 + u;
+                        uint2 h, l;
+                        split2(xe[u].x, xe[u].y, h.x, l.x);
+                        split2(xe[u].z, xe[u].w, h.y, l.y);
+                        const uint32_t off = (uint32_t)(lane >> 4) * IMG + img_off(r, (lane & 15) >> 1) + (lane & 1) * 8;
+                        *reinterpret_cast<uint2*>(s.img_e[0] + off) = h;
+                        *reinterpret_cast<uint2*>(s.img_e[2] + off) = l;
+                        const float4 p = make_float4((xr[u].x + xc[u].x) * ps, (xr[u].y + xc[u].y) * ps,
+                                                     (xr[u].z + xc[u].z) * ps, (xr[u].w + xc[u].w) * ps);
+                        *reinterpret_cast<float4*>(s.img_p[0] + (uint32_t)(lane >> 3) * IMG + img_off(r, lane & 7)) = p;
+                    }
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(leader_in_full);
+            }
+        }
+    } else {
+        setmaxnreg_dec<kRegsMisc>();
+        if (warp == 12 && rank == 0) {
+            // ================================================================== MMA / copy issuer (leader CTA)
+            // both CTAs' weights are in place once in_full completes (every loader warp waited on its w_full)
+            const uint32_t idesc = idesc_f16(256, 128);
+            // descriptors differ only in their 14-bit start-address field (byte address >> 4): add offsets to a base
+            const uint64_t w_desc = make_desc_sw128(smem_u32(s.w[0]));
+            const uint64_t e_desc = make_desc_sw128(smem_u32(s.img_e[0]));
+            const uint64_t p_desc = make_desc_sw128(smem_u32(s.img_p[0]));
+            uint32_t g = 0, n_chain[2] = {0, 0}, n_ar[2] = {0, 0};
+            for (int64_t up = up0; up < n_up; up += up_stride) {
+                const int maxdeg = pair_maxdeg(a, up, lane);
+                for (int j0 = 0; j0 < maxdeg; j0 += 2) {
+                    const int nch = min(2, maxdeg - j0);
+                    for (int l = 0; l < nl; ++l) {
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            if (c >= nch) continue;
+                            const uint32_t d_col = tmem + 256u * c, ah = d_col + 128u, al = d_col + 192u;
+                            if (l == 0) {
+                                if (lane == 0) {
+                                    mbar_wait<true>(&s.d_free[c], (n_chain[c] + 1) & 1);
+                                    mbar_wait<true>(&s.in_full, g & 1);
+                                    tc_fence_after();
+#pragma unroll 1
+                                    for (int i = 0; i < 16; ++i)          // P_r[src] + P_c[tgt] -> accumulator (fp32, 8 columns per copy)
+                                        tmem_cp_128x256b<2>(d_col + 8 * i, p_desc + (uint64_t)(((i >> 2) * IMG + (i & 3) * 32) >> 4));
+#pragma unroll 1
+                                    for (int i = 0; i < 8; ++i) {         // e (hi, lo) -> A operand (16 k per copy)
+                                        const uint64_t off = (uint64_t)(((i >> 2) * IMG + (i & 3) * 32) >> 4);
+                                        tmem_cp_128x256b<2>(ah + 8 * i, e_desc + off);
+                                        tmem_cp_128x256b<2>(al + 8 * i, e_desc + off + (uint64_t)((2 * IMG) >> 4));
+                                    }
+                                    umma_commit<2>(&s.in_empty, 3);
+                                }
+                                ++g;
+                                ++n_chain[c];
+                            } else {
+                                if (lane == 0) {
+                                    mbar_wait<true>(&s.a_ready[c], n_ar[c] & 1);
+                                    tc_fence_after();
+                                }
+                                ++n_ar[c];
+                            }
+                            if (lane == 0) {
+                                const uint64_t wb = w_desc + (uint64_t)((l * 4 * HIMG) >> 4);
+#pragma unroll 1
+                                for (int ks = 0; ks < 8; ++ks) {
+                                    const uint64_t wh = wb + (uint64_t)(((ks >> 2) * 2 * HIMG + (ks & 3) * 32) >> 4);
+                                    const uint64_t wl = wh + (uint64_t)(HIMG >> 4);
+                                    umma_ts<2>(d_col, ah + 8 * ks, wh, idesc, (l == 0 || ks > 0) ? 1u : 0u);
+                                    umma_ts<2>(d_col, al + 8 * ks, wh, idesc, 1u);
+                                    umma_ts<2>(d_col, ah + 8 * ks, wl, idesc, 1u);
+                                }
+                                umma_commit<2>(&s.d_full[c], 3);
+                            }
+                            __syncwarp();
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 12) tmem_dealloc<2>(tmem, 512);
+}
+
+}  // namespace ep
+
+int edge_pair_launch(const EdgeArgs& a, cudaStream_t st) {
+    static bool configured = false;
+    const int smem = (int)sizeof(ep::Smem);
+    if (!configured) {
+        if (cudaFuncSetAttribute(ep::edge_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+            return check_launch("edge_pair_kernel attribute");
+        configured = true;
+    }
+    static int n_sm = 0;
+    if (n_sm == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        if (n_sm <= 0) n_sm = 148;
+    }
+    const int64_t n_units = (a.n_targets + 127) / 128, n_up = (n_units + 1) / 2;
+    const int pairs = (int)std::min<int64_t>(n_up, n_sm / 2);
+    ep::edge_pair_kernel<<<2 * pairs, ep::NT, smem, st>>>(a);
+    count_launch();
+    return check_launch("edge_pair_kernel");
+}
+
+}  // namespace g4c

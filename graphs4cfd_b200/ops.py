@@ -143,6 +143,66 @@ class MlpPack:
         return self._struct
 
 
+class EdgePairPack:
+    """Tensor-core (CTA-pair) operand images of a reference edge MLP whose first Linear takes
+    cat(e, S[src], T[tgt]) (blocks.py:181, 328, 376): linear_1 is split into its e / source / target column
+    blocks sharing one power-of-two scale; the e block and the later layers are stored as pair images for
+    g4c_edge_aggr_fwd, the source / target blocks as fp32 [128, 128] for the per-node products P_r, P_c."""
+
+    def __init__(self, linears: Sequence[Tuple[torch.Tensor, torch.Tensor]], ln=None):
+        assert 2 <= len(linears) <= 3
+        W1, b1 = linears[0]
+        assert W1.shape == (128, 384), "edge MLP of the tensor-core path: hidden 128, input cat(e, s, t)"
+        W1 = W1.detach().float()
+        s1 = weight_scale(W1)
+        self.n_layers = len(linears)
+        self.W_pair, self.inv_scale = [], []
+        pk, inv = pack_weight_pair(W1[:, :128].contiguous(), s1)
+        self.W_pair.append(pk)
+        self.inv_scale.append(inv)
+        self.p_scale = s1
+        self.W1s = W1[:, 128:256].contiguous()
+        self.W1t = W1[:, 256:384].contiguous()
+        self.b1 = b1.detach().float().contiguous().clone()
+        self.bias = [self.b1]
+        for W, b in linears[1:]:
+            assert W.shape == (128, 128)
+            pk, inv = pack_weight_pair(W)
+            self.W_pair.append(pk)
+            self.inv_scale.append(inv)
+            self.bias.append(b.detach().float().contiguous().clone())
+        self.ln = None if ln is None else (ln[0].detach().float().contiguous().clone(),
+                                           ln[1].detach().float().contiguous().clone())
+
+
+def edge_aggr(pack: EdgePairPack, topo: "MpTopo", e_in, P_r, P_c, aggr="mean", act_e=None, want_e=True,
+              e_out=None, agg_out=None):
+    """g4c_edge_aggr_fwd: returns (agg [n_targets,128], e_out|None)."""
+    L.require_cuda_f32(e_in, P_r, P_c)
+    d = L.EdgeDesc()
+    d.n_targets, d.n_edges, d.fixed_k, d.n_layers = topo.n_targets, topo.n_edges, topo.fixed_k, pack.n_layers
+    d.act_e_out, d.aggr = L.ACTS[act_e], (L.AGGR_MEAN if aggr == "mean" else L.AGGR_SUM)
+    d.rowptr = 0 if topo.rowptr is None else topo.rowptr.data_ptr()
+    d.src = topo.src.data_ptr()
+    d.edge_perm = 0 if topo.edge_perm is None else topo.edge_perm.data_ptr()
+    d.tgt_perm = 0 if topo.tgt_perm is None else topo.tgt_perm.data_ptr()
+    if want_e and e_out is None:
+        e_out = torch.empty(topo.n_edges, 128, device=e_in.device, dtype=torch.float32)
+    if agg_out is None:
+        agg_out = torch.empty(P_c.shape[0], 128, device=e_in.device, dtype=torch.float32)
+    d.e_in, d.P_r, d.P_c = e_in.data_ptr(), P_r.data_ptr(), P_c.data_ptr()
+    d.e_out, d.agg_out = (e_out.data_ptr() if want_e else 0), agg_out.data_ptr()
+    for i in range(pack.n_layers):
+        d.W[i] = pack.W_pair[i].data_ptr()
+        d.inv_scale[i] = pack.inv_scale[i]
+        d.bias[i] = pack.bias[i].data_ptr()
+    d.p_scale = pack.p_scale
+    if pack.ln is not None:
+        d.gamma, d.beta = pack.ln[0].data_ptr(), pack.ln[1].data_ptr()
+    L.check(L.lib().g4c_edge_aggr_fwd(C.byref(d), L.stream_ptr()))
+    return agg_out, (e_out if want_e else None)
+
+
 class MpTopo:
     """Static topology of one message-passing level in AGGREGATION order (edges sorted by target).
     fixed_k > 0: target n owns slots [n*k, (n+1)*k) and the caller's order is already that order

@@ -203,11 +203,41 @@ typedef struct {
     float* dst;
 } G4cHaloDesc;
 
+/* Edge half of the message-passing block on the tensor cores (hidden = 128, precision fp16x3), CTA-pair kernel
+ * (csrc/mp_edge_pair.cu).  The first Linear of the edge MLP is split exactly,
+ *     W1 cat(e, S[src], T[tgt]) + b1 = W1e e + P_r[src] + P_c[tgt],   P_r = S W1s^T,  P_c = T W1t^T + b1,
+ * P_r / P_c being per-NODE products made by g4c_rowgemm_fwd.  Computes
+ *     e' = LN(tail(selu(W1e e + P_r[src] + P_c[tgt])))        (blocks.py:181, 328, 376)
+ *     agg[t] = mean|sum over the in-edges of t of e'           (blocks.py:183, 330, 378)
+ * Topology fields have the meaning they have in G4cMpDesc.  Weights are "pair images" (ops.pack_weight_pair:
+ * fp16 hi/lo split of s*W, 64 output rows per CTA, SWIZZLE_128B K-major); W_pair[0] holds the e-columns of
+ * linear_1 and must share the scale s of P (p_scale = s). */
+typedef struct {
+    int64_t n_targets, n_edges;
+    int32_t fixed_k, n_layers, act_e_out, aggr;
+    const int32_t* rowptr;
+    const int32_t* src;
+    const int32_t* edge_perm;
+    const int32_t* tgt_perm;
+    const float* e_in;                /* [n_edges, 128]                                        */
+    const float* P_r;                 /* [*, 128] rows indexed by source id                    */
+    const float* P_c;                 /* [*, 128] rows indexed by target storage row           */
+    float* e_out;                     /* [n_edges, 128] or NULL                                */
+    float* agg_out;                   /* [*, 128] rows indexed by target storage row           */
+    const uint8_t* W[3];              /* pair images of linear_1[:, :128], linear_2, linear_3  */
+    float inv_scale[3];               /* 1/s per layer                                         */
+    float p_scale;                    /* s of layer 1                                          */
+    const float* bias[3];             /* bias[0] unused (folded into P_c)                      */
+    const float* gamma;               /* LayerNorm affine or NULL                              */
+    const float* beta;
+} G4cEdgeDesc;
+
 G4C_API int g4c_version(void);
 G4C_API const char* g4c_last_error(void);
 
 G4C_API int g4c_rowmlp_fwd(const G4cRowMlpDesc* d, void* stream);
 G4C_API int g4c_mp_fwd(const G4cMpDesc* d, void* stream);
+G4C_API int g4c_edge_aggr_fwd(const G4cEdgeDesc* d, void* stream);
 G4C_API int g4c_seg_reduce_fwd(const G4cSegReduceDesc* d, void* stream);
 G4C_API int g4c_project_fwd(const G4cProjectDesc* d, void* stream);
 G4C_API int g4c_edge_to_node_fwd(const G4cEdgeToNodeDesc* d, void* stream);
