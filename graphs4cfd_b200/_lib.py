@@ -54,6 +54,13 @@ class EdgeDesc(C.Structure):
                 ("bias", _f32p * 3), ("gamma", _f32p), ("beta", _f32p)]
 
 
+class RowTcDesc(C.Structure):
+    _fields_ = [("rows", C.c_int64), ("n_segs", C.c_int32), ("n_layers", C.c_int32), ("act_out", C.c_int32),
+                ("out_width", C.c_int32), ("out_stride", C.c_int32), ("res_stride", C.c_int32), ("seg", Seg * MAX_SEGS),
+                ("W", C.c_void_p * 3), ("inv_scale", C.c_float * 3), ("_pad", C.c_int32), ("bias", _f32p * 3),
+                ("gamma", _f32p), ("beta", _f32p), ("out", _f32p), ("residual", _f32p)]
+
+
 class SegReduceDesc(C.Structure):
     _fields_ = [("n_groups", C.c_int64), ("width", C.c_int32), ("aggr", C.c_int32), ("act_out", C.c_int32),
                 ("_pad", C.c_int32), ("ptr", _i32p), ("idx", _i32p), ("x", _f32p), ("out", _f32p)]
@@ -91,6 +98,7 @@ EXPORTS = {
     "g4c_launch_count": (C.c_int64, []),
     "g4c_rowmlp_fwd": (C.c_int, [C.POINTER(RowMlpDesc), C.c_void_p]),
     "g4c_mp_fwd": (C.c_int, [C.POINTER(MpDesc), C.c_void_p]),
+    "g4c_rowmlp_tc_fwd": (C.c_int, [C.POINTER(RowTcDesc), C.c_void_p]),
     "g4c_edge_aggr_fwd": (C.c_int, [C.POINTER(EdgeDesc), C.c_void_p]),
     "g4c_seg_reduce_fwd": (C.c_int, [C.POINTER(SegReduceDesc), C.c_void_p]),
     "g4c_project_fwd": (C.c_int, [C.POINTER(ProjectDesc), C.c_void_p]),

@@ -115,6 +115,29 @@ int g4c_mp_fwd(const G4cMpDesc* d, void* stream) {
     return mp_tc_dispatch(*d, st);
 }
 
+int g4c_rowmlp_tc_fwd(const G4cRowTcDesc* d, void* stream) {
+    if (!d) { set_error("g4c_rowmlp_tc_fwd: NULL descriptor"); return G4C_EINVAL; }
+    if (d->rows < 0 || d->n_segs < 1 || d->n_segs > G4C_MAX_SEGS || d->n_layers < 1 || d->n_layers > 3) {
+        set_error("g4c_rowmlp_tc_fwd: rows=%lld n_segs=%d n_layers=%d", (long long)d->rows, d->n_segs, d->n_layers); return G4C_EINVAL; }
+    for (int s = 0; s < d->n_segs; ++s) {
+        const G4cSeg& sg = d->seg[s];
+        if (!sg.ptr || sg.stride < sg.width) { set_error("g4c_rowmlp_tc_fwd: bad segment %d", s); return G4C_EINVAL; }
+        if (sg.width == 128) {
+            if (!aligned16(sg.ptr) || (sg.stride & 3)) { set_error("g4c_rowmlp_tc_fwd: wide segment %d must be 16-byte aligned", s); return G4C_EINVAL; }
+        } else if (sg.width < 1 || sg.width > 16) { set_error("g4c_rowmlp_tc_fwd: segment width %d must be 128 or 1..16", sg.width); return G4C_EUNSUPPORTED; }
+    }
+    if (d->out_width != 128 && (d->out_width < 1 || d->out_width > 15)) { set_error("g4c_rowmlp_tc_fwd: out_width=%d must be 128 or 1..15", d->out_width); return G4C_EUNSUPPORTED; }
+    if (d->out_width != 128 && d->gamma) { set_error("g4c_rowmlp_tc_fwd: layer_norm on a narrow output is unsupported"); return G4C_EUNSUPPORTED; }
+    if (d->out_width == 128 && d->residual) { set_error("g4c_rowmlp_tc_fwd: residual is only supported on a narrow output"); return G4C_EUNSUPPORTED; }
+    if (!d->out || d->out_stride < d->out_width) { set_error("g4c_rowmlp_tc_fwd: bad out"); return G4C_EINVAL; }
+    if (d->out_width == 128 && ((reinterpret_cast<uintptr_t>(d->out) & 31) || (d->out_stride & 7))) { set_error("g4c_rowmlp_tc_fwd: out must be 32-byte aligned"); return G4C_EINVAL; }
+    for (int l = 0; l < d->n_layers; ++l)
+        if (!d->W[l] || !aligned16(d->W[l]) || !d->bias[l]) { set_error("g4c_rowmlp_tc_fwd: bad weights at layer %d", l + 1); return G4C_EINVAL; }
+    if ((d->gamma == nullptr) != (d->beta == nullptr)) { set_error("g4c_rowmlp_tc_fwd: gamma/beta must both be set or NULL"); return G4C_EINVAL; }
+    if (d->rows == 0) return G4C_OK;
+    return row_pair_launch(*d, static_cast<cudaStream_t>(stream));
+}
+
 int g4c_edge_aggr_fwd(const G4cEdgeDesc* d, void* stream) {
     if (!d) { set_error("g4c_edge_aggr_fwd: NULL descriptor"); return G4C_EINVAL; }
     if (d->n_targets < 0 || d->n_edges < 0 || d->n_edges > 0x7fffffffLL || d->n_targets > 0x7fffffffLL) { set_error("g4c_edge_aggr_fwd: bad sizes"); return G4C_EINVAL; }

@@ -26,20 +26,13 @@
 // Two chains (even / odd slots) alternate so that the MMAs of one overlap the epilogue of the other.
 // TMEM: chain c uses columns [256c, 256c+128) accumulator, [256c+128, +64) A hi, [256c+192, +64) A lo.
 #include <algorithm>
-#include "tc2_core.cuh"
-#include "mp_pair.h"
+#include "pair_common.cuh"
 
 namespace g4c {
 namespace ep {
 
 using namespace tc2;
-
-constexpr int H = 128;
-constexpr int IMG = 128 * 128;
-constexpr int HIMG = 64 * 128;
-constexpr int NT = 512;
-constexpr int NEPI = 256;
-constexpr int kRegsEpi = 200, kRegsLoad = 72, kRegsMisc = 40;
+using namespace pairk;
 
 struct Smem {
     uint8_t w[3][4 * HIMG];          // layer l: K-block 0 hi | lo, K-block 1 hi | lo (64-row images)
@@ -54,19 +47,6 @@ struct Smem {
 };
 
 static_assert(sizeof(Smem) <= 232448, "edge kernel shared memory exceeds the 227 KiB opt-in limit");
-
-__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory"); }
-
-template <int N>
-__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
-template <int N>
-__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
-
-__device__ __forceinline__ void stg256(float* p, const float* v) {
-    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]),
-                 "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
-                 : "memory");
-}
 
 // largest in-degree over the (up to) 256 targets of unit pair `up`; executed by a full warp
 __device__ __forceinline__ int pair_maxdeg(const EdgeArgs& a, int64_t up, int lane) {
@@ -94,30 +74,6 @@ __device__ __forceinline__ RowMeta row_meta(const EdgeArgs& a, int64_t n) {
         r.trow = a.tgt_perm ? a.tgt_perm[n] : (int)n;
     }
     return r;
-}
-
-// ---------------------------------------------------------------------------------------------- epilogues
-// hidden layer: x = selu(acc*inv (+ bias)); written as fp16 (hi, lo) A operand columns of this thread's row
-__device__ __forceinline__ void epilogue_hidden(uint32_t d_addr, uint32_t ah_addr, uint32_t al_addr, float inv,
-                                                const float* __restrict__ bias) {
-#pragma unroll
-    for (int c0 = 0; c0 < 64; c0 += 32) {
-        float v[32];
-        tmem_ld32f(d_addr + c0, v);
-        uint32_t hi[16], lo[16];
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (bias) b = __ldg(reinterpret_cast<const float4*>(bias + c0 + i));
-            const float x0 = selu_fast(fmaf(v[i], inv, b.x)), x1 = selu_fast(fmaf(v[i + 1], inv, b.y));
-            const float x2 = selu_fast(fmaf(v[i + 2], inv, b.z)), x3 = selu_fast(fmaf(v[i + 3], inv, b.w));
-            split2(x0, x1, hi[i / 2], lo[i / 2]);
-            split2(x2, x3, hi[i / 2 + 1], lo[i / 2 + 1]);
-        }
-        tmem_st16(ah_addr + c0 / 2, hi);
-        tmem_st16(al_addr + c0 / 2, lo);
-    }
-    tmem_wait_st();
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_pair_kernel(const EdgeArgs a) {

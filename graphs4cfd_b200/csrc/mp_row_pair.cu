@@ -1,0 +1,387 @@
+// mp_row_pair.cu — row-tile MLP on CTA pairs (cta_group::2), hidden = 128, fp16x3: the node model of the
+// message-passing block (blocks.py:185), encoders / decoders, the DownMP / UpMP MLPs, and the bare Linear that
+// makes the per-node products P_r, P_c of the split edge model (g4c_rowmlp_tc_fwd).
+//
+// Same machinery as mp_edge_pair.cu — weights resident in shared memory as half images per CTA, A operands and
+// accumulators in TMEM, loader warps + tcgen05.cp as the row -> lane transposer, two chains alternating so the
+// MMAs of one tile overlap the epilogue of the other — with these differences:
+//   * a "slot" is a pair-tile (256 consecutive rows, 128 per CTA); the tiles a pair owns alternate chains;
+//   * layer 1 consumes the concatenated input K-block by K-block (64 columns each, or one K = 16 step for a
+//     narrow segment) through a ring of (hi, lo) image stages, so any number of segments streams through the
+//     same 64 TMEM columns of A (K-block b uses half b & 1);
+//   * the last layer is either 128 wide (optional LayerNorm, activation, 256-bit row stores) or narrower than
+//     16 (an N = 16 MMA; bias, optional residual, scalar stores: the decoder, nn/mus_gnn.py:369-373).
+#include <algorithm>
+#include "pair_common.cuh"
+
+namespace g4c {
+namespace rp {
+
+using namespace tc2;
+using namespace pairk;
+
+constexpr int MAX_KB = 6;
+constexpr int STAGE = 2 * IMG;          // hi image | lo image of one K-block
+
+struct KBlock {
+    const float* ptr;
+    const int32_t* gather;
+    int32_t stride, col0, width;        // width 64 (half of a wide segment) or 1..16 (narrow segment)
+    float scale;
+};
+
+struct Args {
+    G4cRowTcDesc d;
+    KBlock kb[MAX_KB];
+    int32_t n_kb, n_stage;
+    uint32_t w_off[3];                  // byte offset of each layer's images in the weight region
+    uint32_t w_bytes, ring_off, tail_off;
+    int64_t n_pt;                       // pair-tiles
+};
+
+struct Tail {
+    float part[2][2][128];
+    uint64_t w_full;
+    uint64_t full[4], empty[4];         // full: leader, 8 loader warps of the pair; empty: local, multicast commit
+    uint64_t a_ready[2], d_free[2];     // leader, 16 epilogue warps of the pair
+    uint64_t d_full[2];                 // local, multicast commit
+    uint32_t tmem_base;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) row_pair_kernel(const Args a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    Tail& s = *reinterpret_cast<Tail*>(smem + a.tail_off);
+    uint8_t* ring = smem + a.ring_off;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_ctarank();
+    const G4cRowTcDesc& d = a.d;
+    const int nl = d.n_layers, NS = a.n_stage, NKB = a.n_kb;
+    const bool narrow_out = d.out_width != H;
+    const int64_t pt0 = blockIdx.x >> 1, pt_stride = gridDim.x >> 1;
+
+    if (tid == 0) {
+        mbar_init(&s.w_full, 1);
+        for (int i = 0; i < 4; ++i) { mbar_init(&s.full[i], 8); mbar_init(&s.empty[i], 1); }
+        for (int c = 0; c < 2; ++c) {
+            mbar_init(&s.a_ready[c], 16);
+            mbar_init(&s.d_free[c], 16);
+            mbar_init(&s.d_full[c], 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 12) { tmem_alloc<2>(&s.tmem_base, 512); tmem_relinquish<2>(); }
+    if (tid == 0) {
+        // this CTA's half of every layer: layer l is stored [rank][...] in global memory
+        mbar_arrive_expect_tx(&s.w_full, a.w_bytes);
+        for (int l = 0; l < nl; ++l) {
+            const uint32_t bytes = (l + 1 < nl ? a.w_off[l + 1] : a.w_bytes) - a.w_off[l];
+            bulk_g2s(smem + a.w_off[l], d.W[l] + (size_t)rank * bytes, bytes, &s.w_full);
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem = s.tmem_base;
+
+    if (warp < 8) {
+        // ====================================================================== epilogue warps
+        setmaxnreg_inc<kRegsEpi>();
+        const int row = (warp & 3) * 32 + lane, half = warp >> 2;
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        const uint32_t leader_a_ready[2] = {mapa(smem_u32(&s.a_ready[0]), 0), mapa(smem_u32(&s.a_ready[1]), 0)};
+        const uint32_t leader_d_free[2] = {mapa(smem_u32(&s.d_free[0]), 0), mapa(smem_u32(&s.d_free[1]), 0)};
+        uint32_t n_dfull[2] = {0, 0};
+        const float* gamma = d.gamma ? d.gamma + half * 64 : nullptr;
+        const float* beta = d.beta ? d.beta + half * 64 : nullptr;
+
+        for (int64_t ptb = pt0; ptb < a.n_pt; ptb += 2 * pt_stride) {
+            const int nch = (ptb + pt_stride < a.n_pt) ? 2 : 1;
+            for (int l = 0; l < nl; ++l) {
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    if (c >= nch) continue;
+                    const int64_t R = ((ptb + c * pt_stride) * 2 + rank) * 128 + row;     // this thread's global row
+                    const uint32_t d_addr = tmem + lane_base + 256u * c + 64u * half;
+                    mbar_wait(&s.d_full[c], n_dfull[c] & 1);
+                    ++n_dfull[c];
+                    tc_fence_after();
+                    if (l < nl - 1) {
+                        epilogue_hidden(d_addr, tmem + lane_base + 256u * c + 128u + 32u * half,
+                                        tmem + lane_base + 256u * c + 192u + 32u * half, d.inv_scale[l], d.bias[l] + half * 64);
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(leader_a_ready[c]);
+                    } else if (narrow_out) {
+                        // ---- last layer narrower than 16: columns 0..out_width-1 of the N = 32 accumulator
+                        float y[16];
+                        if (half == 0) tmem_ld16f(tmem + lane_base + 256u * c, y);
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(leader_d_free[c]);
+                        if (half == 0 && R < d.rows) {
+                            const float inv = d.inv_scale[l];
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                if (i < d.out_width) {
+                                    float v = fmaf(y[i], inv, __ldg(d.bias[l] + i));
+                                    v = apply_act_fast(v, d.act_out);
+                                    if (d.residual) v += __ldg(d.residual + (size_t)R * d.res_stride + i);
+                                    d.out[(size_t)R * d.out_stride + i] = v;
+                                }
+                            }
+                        }
+                    } else {
+                        // ---- last layer 128 wide: LayerNorm, activation, store
+                        float y[64];
+                        const float inv = d.inv_scale[l];
+                        const float* bias = d.bias[l] + half * 64;
+                        tmem_ld32f(d_addr, y);
+                        tmem_ld32f(d_addr + 32, y + 32);
+#pragma unroll
+                        for (int i = 0; i < 64; i += 4) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(bias + i));
+                            y[i] = fmaf(y[i], inv, b.x);
+                            y[i + 1] = fmaf(y[i + 1], inv, b.y);
+                            y[i + 2] = fmaf(y[i + 2], inv, b.z);
+                            y[i + 3] = fmaf(y[i + 3], inv, b.w);
+                        }
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(leader_d_free[c]);
+                        if (gamma) {
+                            float sum = 0.f;
+#pragma unroll
+                            for (int i = 0; i < 64; ++i) sum += y[i];
+                            s.part[0][half][row] = sum;
+                            epi_sync();
+                            const float mean = (s.part[0][0][row] + s.part[0][1][row]) * (1.f / H);
+                            float sq = 0.f;
+#pragma unroll
+                            for (int i = 0; i < 64; ++i) {
+                                y[i] -= mean;
+                                sq = fmaf(y[i], y[i], sq);
+                            }
+                            s.part[1][half][row] = sq;
+                            epi_sync();
+                            const float rstd = 1.f / sqrtf((s.part[1][0][row] + s.part[1][1][row]) * (1.f / H) + kLnEps);
+#pragma unroll
+                            for (int i = 0; i < 64; i += 4) {
+                                const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + i));
+                                const float4 b = __ldg(reinterpret_cast<const float4*>(beta + i));
+                                y[i] = fmaf(y[i] * rstd, g.x, b.x);
+                                y[i + 1] = fmaf(y[i + 1] * rstd, g.y, b.y);
+                                y[i + 2] = fmaf(y[i + 2] * rstd, g.z, b.z);
+                                y[i + 3] = fmaf(y[i + 3] * rstd, g.w, b.w);
+                            }
+                        }
+                        if (R < d.rows) {
+                            float* dst = d.out + (size_t)R * d.out_stride + half * 64;
+#pragma unroll
+                            for (int i = 0; i < 64; i += 8) {
+                                float o[8];
+#pragma unroll
+                                for (int u = 0; u < 8; ++u) o[u] = apply_act_fast(y[i + u], d.act_out);
+                                stg256(dst + i, o);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp < 12) {
+        // ====================================================================== loader warps
+        setmaxnreg_dec<kRegsLoad>();
+        const int lw = warp - 8;
+        const uint32_t leader_full0 = mapa(smem_u32(&s.full[0]), 0);      // full[] is contiguous: + 8 bytes per stage
+        uint32_t g = 0;                       // K-block stages produced so far
+        mbar_wait(&s.w_full, 0);              // full[] is only signalled once this CTA's weights have landed
+        for (int64_t pt = pt0; pt < a.n_pt; pt += pt_stride) {
+            const int64_t R_lane = (pt * 2 + rank) * 128 + lw * 32 + lane;     // the row this lane describes
+            for (int b = 0; b < NKB; ++b, ++g) {
+                const KBlock& kb = a.kb[b];
+                const int st = g % NS;
+                uint8_t* img_hi = ring + (size_t)st * STAGE;
+                uint8_t* img_lo = img_hi + IMG;
+                int64_t src_row = -1;
+                if (R_lane < d.rows) src_row = kb.gather ? (int64_t)kb.gather[R_lane] : R_lane;
+                mbar_wait(&s.empty[st], ((g / NS) + 1) & 1);
+                if (kb.width == 64) {
+                    // two rows per warp instruction: lanes 0-15 one row, lanes 16-31 the next
+                    const int sub = lane >> 4, l16 = lane & 15;
+#pragma unroll 1
+                    for (int i0 = 0; i0 < 32; i0 += 8) {
+                        float4 x[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int64_t sr = __shfl_sync(0xffffffffu, src_row, i0 + 2 * u + sub);
+                            x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (sr >= 0) x[u] = __ldg(reinterpret_cast<const float4*>(kb.ptr + (size_t)sr * kb.stride + kb.col0 + l16 * 4));
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int r = lw * 32 + i0 + 2 * u + sub;
+                            uint2 h, lo;
+                            split2(x[u].x * kb.scale, x[u].y * kb.scale, h.x, lo.x);
+                            split2(x[u].z * kb.scale, x[u].w * kb.scale, h.y, lo.y);
+                            const uint32_t off = img_off(r, l16 >> 1) + (l16 & 1) * 8;
+                            *reinterpret_cast<uint2*>(img_hi + off) = h;
+                            *reinterpret_cast<uint2*>(img_lo + off) = lo;
+                        }
+                    }
+                } else {
+                    // narrow segment: lane = row, one K = 16 step (32 bytes per image row)
+                    const int r = lw * 32 + lane;
+                    uint32_t h[8], lo[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        float x0 = 0.f, x1 = 0.f;
+                        if (src_row >= 0) {
+                            if (2 * i < kb.width) x0 = __ldg(kb.ptr + (size_t)src_row * kb.stride + kb.col0 + 2 * i) * kb.scale;
+                            if (2 * i + 1 < kb.width) x1 = __ldg(kb.ptr + (size_t)src_row * kb.stride + kb.col0 + 2 * i + 1) * kb.scale;
+                        }
+                        split2(x0, x1, h[i], lo[i]);
+                    }
+                    *reinterpret_cast<uint4*>(img_hi + img_off(r, 0)) = make_uint4(h[0], h[1], h[2], h[3]);
+                    *reinterpret_cast<uint4*>(img_hi + img_off(r, 1)) = make_uint4(h[4], h[5], h[6], h[7]);
+                    *reinterpret_cast<uint4*>(img_lo + img_off(r, 0)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    *reinterpret_cast<uint4*>(img_lo + img_off(r, 1)) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(leader_full0 + 8u * (uint32_t)st);
+            }
+        }
+    } else {
+        setmaxnreg_dec<kRegsMisc>();
+        if (warp == 12 && rank == 0) {
+            // ================================================================== MMA / copy issuer (leader CTA)
+            const uint32_t idesc = idesc_f16(256, 128), idesc_narrow = idesc_f16(256, 32);
+            const uint64_t w_desc = make_desc_sw128(smem_u32(smem));
+            const uint64_t ring_desc = make_desc_sw128(smem_u32(ring));
+            uint32_t g = 0, n_chain[2] = {0, 0}, n_ar[2] = {0, 0};
+            for (int64_t ptb = pt0; ptb < a.n_pt; ptb += 2 * pt_stride) {
+                const int nch = (ptb + pt_stride < a.n_pt) ? 2 : 1;
+                for (int l = 0; l < nl; ++l) {
+                    const bool narrow_layer = narrow_out && l == nl - 1;
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        if (c >= nch) continue;
+                        const uint32_t d_col = tmem + 256u * c, ah = d_col + 128u, al = d_col + 192u;
+                        if (l == 0) {
+                            if (lane == 0) mbar_wait<true>(&s.d_free[c], (n_chain[c] + 1) & 1);
+                            ++n_chain[c];
+                            for (int b = 0; b < NKB; ++b, ++g) {
+                                if (lane == 0) {
+                                    const int st = g % NS;
+                                    const int nks = a.kb[b].width == 64 ? 4 : 1;
+                                    const uint32_t hb = 32u * (b & 1);
+                                    mbar_wait<true>(&s.full[st], (g / NS) & 1);
+                                    tc_fence_after();
+                                    const uint64_t sd = ring_desc + (uint64_t)((st * STAGE) >> 4);
+#pragma unroll 1
+                                    for (int j = 0; j < nks; ++j) {
+                                        tmem_cp_128x256b<2>(ah + hb + 8 * j, sd + (uint64_t)((32 * j) >> 4));
+                                        tmem_cp_128x256b<2>(al + hb + 8 * j, sd + (uint64_t)((IMG + 32 * j) >> 4));
+                                    }
+                                    const uint64_t wb = w_desc + (uint64_t)((a.w_off[0] + b * 2 * HIMG) >> 4);
+#pragma unroll 1
+                                    for (int j = 0; j < nks; ++j) {
+                                        const uint64_t wh = wb + (uint64_t)((32 * j) >> 4), wl = wh + (uint64_t)(HIMG >> 4);
+                                        umma_ts<2>(d_col, ah + hb + 8 * j, wh, idesc, (b > 0 || j > 0) ? 1u : 0u);
+                                        umma_ts<2>(d_col, al + hb + 8 * j, wh, idesc, 1u);
+                                        umma_ts<2>(d_col, ah + hb + 8 * j, wl, idesc, 1u);
+                                    }
+                                    umma_commit<2>(&s.empty[st], 3);
+                                }
+                            }
+                            if (lane == 0) umma_commit<2>(&s.d_full[c], 3);
+                        } else {
+                            if (lane == 0) {
+                                mbar_wait<true>(&s.a_ready[c], n_ar[c] & 1);
+                                tc_fence_after();
+                                // K = 128 from the A operand the epilogue wrote; 64-row images, or 16-row images (N = 32)
+                                const uint32_t kb_bytes = narrow_layer ? 4096u : 2u * HIMG, lo_off = narrow_layer ? 2048u : (uint32_t)HIMG;
+                                const uint64_t wb = w_desc + (uint64_t)(a.w_off[l] >> 4);
+                                const uint32_t id = narrow_layer ? idesc_narrow : idesc;
+#pragma unroll 1
+                                for (int ks = 0; ks < 8; ++ks) {
+                                    const uint64_t wh = wb + (uint64_t)(((ks >> 2) * kb_bytes + (ks & 3) * 32) >> 4);
+                                    const uint64_t wl = wh + (uint64_t)(lo_off >> 4);
+                                    umma_ts<2>(d_col, ah + 8 * ks, wh, id, ks > 0 ? 1u : 0u);
+                                    umma_ts<2>(d_col, al + 8 * ks, wh, id, 1u);
+                                    umma_ts<2>(d_col, ah + 8 * ks, wl, id, 1u);
+                                }
+                                umma_commit<2>(&s.d_full[c], 3);
+                            }
+                            ++n_ar[c];
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 12) tmem_dealloc<2>(tmem, 512);
+}
+
+}  // namespace rp
+
+int row_pair_launch(const G4cRowTcDesc& d, cudaStream_t st) {
+    rp::Args a;
+    a.d = d;
+    a.n_kb = 0;
+    for (int sgi = 0; sgi < d.n_segs; ++sgi) {
+        const G4cSeg& sg = d.seg[sgi];
+        const int nblk = sg.width == 128 ? 2 : 1;
+        for (int h = 0; h < nblk; ++h) {
+            if (a.n_kb >= rp::MAX_KB) { set_error("g4c_rowmlp_tc_fwd: more than %d K-blocks", rp::MAX_KB); return G4C_EUNSUPPORTED; }
+            rp::KBlock& kb = a.kb[a.n_kb++];
+            kb.ptr = sg.ptr; kb.gather = sg.gather; kb.stride = sg.stride; kb.scale = sg.scale;
+            kb.col0 = 64 * h;
+            kb.width = sg.width == 128 ? 64 : sg.width;
+        }
+    }
+    const bool narrow = d.out_width != 128;
+    if (narrow && d.n_layers == 1) { set_error("g4c_rowmlp_tc_fwd: a single narrow Linear is unsupported"); return G4C_EUNSUPPORTED; }
+    uint32_t off = 0;
+    for (int l = 0; l < d.n_layers; ++l) {
+        a.w_off[l] = off;
+        const bool narrow_layer = narrow && l == d.n_layers - 1;
+        const uint32_t per_kb = narrow_layer ? 4096u : 2u * pairk::HIMG;
+        off += per_kb * (l == 0 ? (uint32_t)a.n_kb : 2u);
+    }
+    a.w_bytes = off;
+    a.ring_off = (off + 1023u) & ~1023u;
+    const uint32_t tail = (uint32_t)sizeof(rp::Tail);
+    const int avail = pairk::kMaxSmem - (int)a.ring_off - (int)tail - 16;
+    a.n_stage = std::min(4, avail / rp::STAGE);
+    if (a.n_stage < 2) { set_error("g4c_rowmlp_tc_fwd: weights (%u bytes per CTA) leave no room for the input ring", off); return G4C_EUNSUPPORTED; }
+    a.tail_off = a.ring_off + (uint32_t)a.n_stage * rp::STAGE;
+    a.tail_off = (a.tail_off + 15u) & ~15u;
+    const int smem = (int)(a.tail_off + tail);
+    const int64_t n_pt = (d.rows + 255) / 256;
+    a.n_pt = n_pt;
+    static int configured_smem = 0;
+    if (smem > configured_smem) {
+        if (cudaFuncSetAttribute(rp::row_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+            return check_launch("row_pair_kernel attribute");
+        configured_smem = smem;
+    }
+    static int n_sm = 0;
+    if (n_sm == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        if (n_sm <= 0) n_sm = 148;
+    }
+    const int pairs = (int)std::min<int64_t>(n_pt, n_sm / 2);
+    rp::row_pair_kernel<<<2 * pairs, pairk::NT, smem, st>>>(a);
+    count_launch();
+    return check_launch("row_pair_kernel");
+}
+
+}  // namespace g4c

@@ -55,10 +55,10 @@ def weight_scale(W: torch.Tensor) -> float:
 
 
 def pack_weight_pair(W: torch.Tensor, s: Optional[float] = None):
-    """Operand images of W [128, K] for a CTA pair (cta_group::2): CTA r holds output rows [64r, 64r+64).
-    Layout [r][kb][hi|lo][64 rows][64 fp16] (8 KiB images).  Returns (uint8 tensor, 1/s)."""
+    """Operand images of W [N, K] (N = 128 or 32) for a CTA pair (cta_group::2): CTA r holds output rows
+    [N/2*r, N/2*(r+1)).  Layout [r][kb][hi|lo][N/2 rows][64 fp16].  Returns (uint8 tensor, 1/s)."""
     N, K = W.shape
-    assert N == 128 and K % 64 == 0
+    assert N in (128, 32) and K % 64 == 0
     W = W.detach().float()
     s = weight_scale(W) if s is None else s
     Ws = W * s
@@ -66,8 +66,8 @@ def pack_weight_pair(W: torch.Tensor, s: Optional[float] = None):
     lo = (Ws - hi.float()).half()
     parts = []
     for r in range(2):
-        h = _swizzled_images(hi[64 * r:64 * r + 64].contiguous())      # [kb, 64, 64]
-        l = _swizzled_images(lo[64 * r:64 * r + 64].contiguous())
+        h = _swizzled_images(hi[N // 2 * r:N // 2 * (r + 1)].contiguous())      # [kb, N/2, 64]
+        l = _swizzled_images(lo[N // 2 * r:N // 2 * (r + 1)].contiguous())
         parts.append(torch.stack([h, l], dim=1))                        # [kb, 2, 64, 64]
     pack = torch.stack(parts, dim=0).contiguous()                       # [2, kb, 2, 64, 64]
     return pack.view(torch.uint8).reshape(-1), 1.0 / s
@@ -87,6 +87,9 @@ class MlpPack:
         for W, _ in linears[:-1]:
             if W.shape[0] != self.hidden:
                 raise RuntimeError("graphs4cfd_b200: all hidden widths of an MLP must be equal")
+        self._linears = [(W.detach().float(), b.detach().float()) for W, b in linears]
+        self._ln_raw = None if ln is None else (ln[0].detach().float(), ln[1].detach().float())
+        self._tc_row, self._tc_edge = {}, None
         self.W_t, self.b = [], []
         for i, (W, b) in enumerate(linears):
             W = W.detach().float()
@@ -97,13 +100,31 @@ class MlpPack:
                                            ln[1].detach().float().contiguous().clone())
         L.require_cuda_f32(*self.W_t, *self.b)
         self._struct = None
-        # tensor-core images (hidden = 128 only; the first layer's K must be a multiple of 64)
-        self.W_pack, self.w_inv_scale = [], []
-        if self.hidden == 128 and self.out_width == 128 and self.in_width % 64 == 0:
-            for W, _ in linears:
-                pk, inv = pack_weight_fp16x2(W)
-                self.W_pack.append(pk)
-                self.w_inv_scale.append(inv)
+        self.W_pack, self.w_inv_scale = [], []      # (first-generation single-CTA images: no longer produced)
+
+    # ---- tensor-core (fp16x3, CTA-pair kernels) operand images, built on first use
+    def tc_row_ok(self, seg_widths) -> bool:
+        return (self.hidden == 128 and sum(seg_widths) == self.in_width
+                and all(w == 128 or 1 <= w <= 16 for w in seg_widths)
+                and sum(2 if w == 128 else 1 for w in seg_widths) <= 6
+                and (self.out_width == 128 or (self.out_width < 16 and self.ln is None and self.n_layers > 1)))
+
+    def tc_row(self, seg_widths) -> "RowPairPack":
+        key = tuple(seg_widths)
+        if key not in self._tc_row:
+            self._tc_row[key] = RowPairPack(self._linears, list(seg_widths), self._ln_raw)
+        return self._tc_row[key]
+
+    def tc_edge_ok(self) -> bool:
+        return self.hidden == 128 and self.in_width == 384 and self.out_width == 128
+
+    def tc_edge(self):
+        """(EdgePairPack, projection of the source features, projection of the target features)."""
+        if self._tc_edge is None:
+            ep = EdgePairPack(self._linears, self._ln_raw)
+            zero = torch.zeros_like(ep.b1)
+            self._tc_edge = (ep, RowPairPack([(ep.W1s, zero)], [128]), RowPairPack([(ep.W1t, ep.b1)], [128]))
+        return self._tc_edge
 
     @classmethod
     def from_module(cls, mlp_module):
@@ -175,6 +196,72 @@ class EdgePairPack:
                                            ln[1].detach().float().contiguous().clone())
 
 
+class RowPairPack:
+    """Tensor-core (CTA-pair) operand images of a reference ``MLP`` (blocks.py:129-144) or of a bare Linear,
+    for g4c_rowmlp_tc_fwd.  ``seg_widths`` are the widths of the concatenated input segments in order (each 128
+    or <= 16): linear_1's columns are re-laid out K-block by K-block (narrow segments zero-padded to 64)."""
+
+    def __init__(self, linears: Sequence[Tuple[torch.Tensor, torch.Tensor]], seg_widths: Sequence[int], ln=None):
+        assert 1 <= len(linears) <= 3
+        dev = linears[0][0].device
+        W1 = linears[0][0].detach().float()
+        assert W1.shape[0] == 128 and W1.shape[1] == sum(seg_widths), "hidden width 128 and matching input width"
+        cols, c0 = [], 0
+        for w in seg_widths:
+            assert w == 128 or 1 <= w <= 16, "segments must be 128 wide or at most 16"
+            blk = W1[:, c0:c0 + w]
+            if w != 128:
+                blk = torch.cat([blk, torch.zeros(128, 64 - w, device=dev)], dim=1)
+            cols.append(blk)
+            c0 += w
+        self.seg_widths = list(seg_widths)
+        self.n_layers = len(linears)
+        self.out_width = int(linears[-1][0].shape[0])
+        self.W_pair, self.inv_scale, self.bias = [], [], []
+        for i, (W, b) in enumerate(linears):
+            W = torch.cat(cols, dim=1).contiguous() if i == 0 else W.detach().float()
+            b = b.detach().float()
+            if i == self.n_layers - 1 and self.out_width != 128:
+                assert self.out_width < 16 and i > 0, "narrow output: at most 15 columns, not on a single Linear"
+                W = torch.cat([W, torch.zeros(32 - self.out_width, W.shape[1], device=dev)], dim=0)
+                b = torch.cat([b, torch.zeros(32 - self.out_width, device=dev)])
+            else:
+                assert W.shape[0] == 128
+            pk, inv = pack_weight_pair(W.contiguous())
+            self.W_pair.append(pk)
+            self.inv_scale.append(inv)
+            self.bias.append(b.contiguous().clone())
+        self.ln = None if ln is None else (ln[0].detach().float().contiguous().clone(),
+                                           ln[1].detach().float().contiguous().clone())
+
+
+def rowmlp_tc(pack: RowPairPack, segs, rows: Optional[int] = None, act=None, out=None, residual=None):
+    """g4c_rowmlp_tc_fwd: out = act([LN](MLP(cat(segs)))) [+ residual]; segs = [(tensor, gather|None, scale)]."""
+    d = L.RowTcDesc()
+    tens = [s[0] for s in segs]
+    assert [int(t.shape[1]) for t in tens] == pack.seg_widths, "segment widths do not match the packed linear_1"
+    if rows is None:
+        rows = int(segs[0][1].numel()) if segs[0][1] is not None else int(tens[0].shape[0])
+    d.rows, d.n_segs, d.n_layers, d.act_out, d.out_width = rows, len(segs), pack.n_layers, L.ACTS[act], pack.out_width
+    for i, (t, gather, scale) in enumerate(segs):
+        if not (t.is_cuda and t.dtype == torch.float32 and t.stride(1) == 1):
+            raise RuntimeError("rowmlp_tc: segments must be fp32 CUDA tensors with unit column stride")
+        d.seg[i] = _seg_struct(t, gather, scale)
+    for i in range(pack.n_layers):
+        d.W[i] = pack.W_pair[i].data_ptr()
+        d.inv_scale[i] = pack.inv_scale[i]
+        d.bias[i] = pack.bias[i].data_ptr()
+    if pack.ln is not None:
+        d.gamma, d.beta = pack.ln[0].data_ptr(), pack.ln[1].data_ptr()
+    if out is None:
+        out = torch.empty(rows, pack.out_width, device=tens[0].device, dtype=torch.float32)
+    d.out, d.out_stride = out.data_ptr(), int(out.stride(0))
+    if residual is not None:
+        d.residual, d.res_stride = residual.data_ptr(), int(residual.stride(0))
+    L.check(L.lib().g4c_rowmlp_tc_fwd(C.byref(d), L.stream_ptr()))
+    return out
+
+
 def edge_aggr(pack: EdgePairPack, topo: "MpTopo", e_in, P_r, P_c, aggr="mean", act_e=None, want_e=True,
               e_out=None, agg_out=None):
     """g4c_edge_aggr_fwd: returns (agg [n_targets,128], e_out|None)."""
@@ -238,8 +325,17 @@ def _seg_struct(t: torch.Tensor, gather, scale) -> L.Seg:
     return s
 
 
-def rowmlp(pack: MlpPack, segs, rows: Optional[int] = None, act=None, out=None, residual=None):
-    """out = act(MLP(cat(segs, dim=-1)) [+ residual]); segs = [(tensor[*, w], gather_idx|None, scale)]."""
+def rowmlp(pack: MlpPack, segs, rows: Optional[int] = None, act=None, out=None, residual=None, precision="fp32"):
+    """out = act(MLP(cat(segs, dim=-1)) [+ residual]); segs = [(tensor[*, w], gather_idx|None, scale)].
+    precision "fp16x3" runs the tensor-core row kernel (hidden 128); "fp32" the CUDA-core one."""
+    if precision == "fp16x3":
+        widths = [int(s[0].shape[1]) for s in segs]
+        if not pack.tc_row_ok(widths) or (residual is not None and pack.out_width == 128):
+            raise RuntimeError(f"rowmlp: precision fp16x3 does not support hidden={pack.hidden}, segments={widths}, "
+                               f"out_width={pack.out_width}; use precision='fp32'")
+        return rowmlp_tc(pack.tc_row(widths), segs, rows=rows, act=act, out=out, residual=residual)
+    if precision != "fp32":
+        raise RuntimeError(f"rowmlp: unknown precision {precision!r}")
     d = L.RowMlpDesc()
     tens = [s[0] for s in segs]
     for t in tens:
@@ -261,10 +357,26 @@ def rowmlp(pack: MlpPack, segs, rows: Optional[int] = None, act=None, out=None, 
 
 
 def mp(edge_pack: MlpPack, node_pack: MlpPack, topo: MpTopo, e_in, src_feat, tgt_feat, aggr="mean",
-       act_e=None, act_t=None, want_e=True, precision="fp32", e_out=None, t_out=None):
-    """Fused message-passing block (g4c_mp_fwd).  Returns (t_out, e_out|None)."""
+       act_e=None, act_t=None, want_e=True, precision="fp32", e_out=None, t_out=None, ws=None):
+    """Message-passing block.  precision "fp32": one fused CUDA-core kernel (g4c_mp_fwd); "fp16x3": the tensor-core
+    path = per-node products of the split first edge layer (g4c_rowmlp_tc_fwd x2), fused edge MLP + aggregation
+    (g4c_edge_aggr_fwd), node model (g4c_rowmlp_tc_fwd).  ``ws`` = optional preallocated (P_r, P_c, agg).
+    Returns (t_out, e_out|None)."""
     L.require_cuda_f32(e_in, src_feat, tgt_feat)
     H = edge_pack.hidden
+    if precision == "fp16x3":
+        if not (edge_pack.tc_edge_ok() and node_pack.tc_row_ok([128, 128])):
+            raise RuntimeError(f"mp: precision fp16x3 needs hidden=128 (got {H}); use precision='fp32'")
+        ep, proj_s, proj_t = edge_pack.tc_edge()
+        dev = e_in.device
+        P_r, P_c, agg = ws if ws is not None else (None, None, None)
+        P_r = rowmlp_tc(proj_s, [(src_feat, None, 1.0)], out=P_r)
+        P_c = rowmlp_tc(proj_t, [(tgt_feat, None, 1.0)], out=P_c)
+        if agg is None:
+            agg = torch.empty(tgt_feat.shape[0], 128, device=dev, dtype=torch.float32)
+        agg, e_out = edge_aggr(ep, topo, e_in, P_r, P_c, aggr=aggr, act_e=act_e, want_e=want_e, e_out=e_out, agg_out=agg)
+        t_out = rowmlp_tc(node_pack.tc_row([128, 128]), [(agg, None, 1.0), (tgt_feat, None, 1.0)], act=act_t, out=t_out)
+        return t_out, e_out
     d = L.MpDesc()
     d.hidden, d.aggr, d.fixed_k = H, (L.AGGR_MEAN if aggr == "mean" else L.AGGR_SUM), topo.fixed_k
     d.act_e_out, d.act_t_out, d.precision = L.ACTS[act_e], L.ACTS[act_t], L.PRECISIONS[precision]

@@ -232,11 +232,38 @@ typedef struct {
     const float* beta;
 } G4cEdgeDesc;
 
+/* Row-tile MLP on the tensor cores (hidden = 128, precision fp16x3), CTA-pair kernel (csrc/mp_row_pair.cu):
+ *     out = act( [LN]( MLP( cat(seg0[g0], seg1[g1], ...) ) ) [+ residual] )
+ * Same role as g4c_rowmlp_fwd (MLP.forward, blocks.py:143, as used by encoders / decoders / DownMP / UpMP /
+ * the node model of GNBlock, blocks.py:185, 229, 285) plus n_layers == 1 (a bare Linear: the per-node products
+ * P_r, P_c of the split edge model).  Segments are 128 wide (two 64-wide K-blocks) or at most 16 wide (one
+ * K-block, zero padded).  W[0] = pair images of linear_1 with its columns laid out K-block by K-block
+ * ([128, 64*n_kblocks], narrow segments padded to 64 columns); W[l] = pair images of the later layers; when
+ * out_width < 16 the last layer's rows are padded to 32 and stored as 16-row images (ops.pack_weight_pair with 32 rows). */
+typedef struct {
+    int64_t rows;
+    int32_t n_segs;                   /* 1..3                                                  */
+    int32_t n_layers;                 /* 1..3                                                  */
+    int32_t act_out;
+    int32_t out_width;                /* 128, or 1..15 (narrow last layer, no LayerNorm)       */
+    int32_t out_stride, res_stride;
+    G4cSeg seg[G4C_MAX_SEGS];
+    const uint8_t* W[3];
+    float inv_scale[3];
+    int32_t _pad;
+    const float* bias[3];
+    const float* gamma;
+    const float* beta;
+    float* out;                       /* [rows, out_width], row stride out_stride floats       */
+    const float* residual;            /* narrow output only: [rows, >= out_width] or NULL      */
+} G4cRowTcDesc;
+
 G4C_API int g4c_version(void);
 G4C_API const char* g4c_last_error(void);
 
 G4C_API int g4c_rowmlp_fwd(const G4cRowMlpDesc* d, void* stream);
 G4C_API int g4c_mp_fwd(const G4cMpDesc* d, void* stream);
+G4C_API int g4c_rowmlp_tc_fwd(const G4cRowTcDesc* d, void* stream);
 G4C_API int g4c_edge_aggr_fwd(const G4cEdgeDesc* d, void* stream);
 G4C_API int g4c_seg_reduce_fwd(const G4cSegReduceDesc* d, void* stream);
 G4C_API int g4c_project_fwd(const G4cProjectDesc* d, void* stream);

@@ -1,0 +1,91 @@
+"""g4c_rowmlp_tc_fwd (CTA-pair tcgen05 row-tile MLP) against an fp64 restatement of MLP.forward
+(graphs4cfd/nn/blocks.py:129-144) on concatenated, optionally gathered / scaled segments — the shapes the
+hot path uses: node model (2 wide segments), DownMP (narrow + wide), UpMP (narrow, gathered wide, wide),
+encoders (narrow only), decoder (narrow output + residual), and the bare Linear of the split edge model.
+Tolerance 2e-5 rel-L2 (22-bit operands, ex2.approx SELU)."""
+import pytest
+import torch
+
+from graphs4cfd_b200 import ops
+
+gpu = pytest.mark.gpu
+F = torch.nn.functional
+
+
+def _lin(i, o, g, dev):
+    return ((torch.rand(o, i, generator=g) * 2 - 1).div(i ** 0.5).to(dev), (torch.rand(o, generator=g) * 2 - 1).div(i ** 0.5).to(dev))
+
+
+def _check(rows, seg_widths, widths, ln, act, gather_seg=None, scales=None, residual=False, seed=0):
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(seed)
+    dims = [sum(seg_widths)] + list(widths)
+    lin = [_lin(dims[i], dims[i + 1], g, dev) for i in range(len(widths))]
+    lnp = ((1 + 0.1 * torch.randn(128, generator=g)).to(dev), (0.1 * torch.randn(128, generator=g)).to(dev)) if ln else None
+    scales = scales or [1.0] * len(seg_widths)
+    segs, cat = [], []
+    for i, w in enumerate(seg_widths):
+        if gather_seg == i:
+            src = torch.randn(rows // 3 + 1, w, generator=g).to(dev)
+            idx = torch.randint(0, src.shape[0], (rows,), generator=g).to(dev).to(torch.int32)
+            segs.append((src, idx, scales[i]))
+            cat.append(src[idx.long()].double() * scales[i])
+        else:
+            t = torch.randn(rows, w, generator=g).to(dev)
+            segs.append((t, None, scales[i]))
+            cat.append(t.double() * scales[i])
+    x = torch.cat(cat, dim=1)
+    for i, (W, b) in enumerate(lin):
+        x = x @ W.double().t() + b.double()
+        if i < len(lin) - 1:
+            x = F.selu(x)
+    if ln:
+        x = F.layer_norm(x, (128,), lnp[0].double(), lnp[1].double(), 1e-5)
+    x = {"selu": F.selu, "tanh": torch.tanh, None: (lambda z: z)}[act](x)
+    res = None
+    if residual:
+        res = torch.randn(rows, widths[-1] + 2, generator=g).to(dev)
+        x = x + res[:, :widths[-1]].double()
+    pack = ops.RowPairPack(lin, seg_widths, lnp)
+    out = ops.rowmlp_tc(pack, segs, rows=rows, act=act, residual=res)
+    torch.cuda.synchronize()
+    err = float((out.double() - x).norm() / x.norm())
+    assert err < 2e-5, f"rel-L2 {err:.3e}"
+
+
+@gpu
+@pytest.mark.parametrize("rows", [1, 255, 256, 1000, 70000])
+def test_node_model(rows):
+    _check(rows, [128, 128], [128, 128, 128], True, "selu")
+
+
+@gpu
+def test_two_layer_and_no_ln():
+    _check(3001, [128], [128, 128], False, None)
+
+
+@gpu
+def test_bare_linear():
+    _check(5000, [128], [128], False, None)
+
+
+@gpu
+def test_down_mlp():
+    _check(4097, [2, 128], [128, 128, 128], True, None)
+
+
+@gpu
+def test_up_mlp_gathered_scaled():
+    _check(9000, [2, 128, 128], [128, 128, 128], True, "tanh", gather_seg=1, scales=[-1.0, 1.0, 1.0])
+
+
+@gpu
+@pytest.mark.parametrize("kin", [2, 3, 5, 16])
+def test_encoder_narrow_input(kin):
+    _check(2500, [kin], [128, 128, 128], True, "selu")
+
+
+@gpu
+@pytest.mark.parametrize("nout", [1, 3])
+def test_decoder_narrow_output_residual(nout):
+    _check(7777, [128], [128, 128, nout], False, None, residual=True)

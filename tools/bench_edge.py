@@ -1,0 +1,58 @@
+"""Times g4c_edge_aggr_fwd alone on a synthetic fixed-k topology (scratch benchmark, not the driver's bench.py).
+    python tools/bench_edge.py [--nodes N] [--k K] [--reps R] [--spread S]"""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from graphs4cfd_b200 import ops  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--nodes", type=int, default=1_000_000)
+ap.add_argument("--k", type=int, default=6)
+ap.add_argument("--reps", type=int, default=10)
+ap.add_argument("--spread", type=int, default=2000, help="sources are drawn within +-spread of the target id")
+ap.add_argument("--layers", type=int, default=3)
+ap.add_argument("--no-e", action="store_true")
+a = ap.parse_args()
+
+dev = torch.device("cuda")
+torch.manual_seed(0)
+n, k = a.nodes, a.k
+col = torch.arange(n, device=dev).repeat_interleave(k)
+row = (col + torch.randint(-a.spread, a.spread + 1, (n * k,), device=dev)).clamp_(0, n - 1)
+dims = [384] + [128] * a.layers
+lin = [((torch.rand(dims[i + 1], dims[i], device=dev) * 2 - 1) / dims[i] ** 0.5,
+        (torch.rand(dims[i + 1], device=dev) * 2 - 1) / dims[i] ** 0.5) for i in range(a.layers)]
+ln = (torch.ones(128, device=dev), torch.zeros(128, device=dev))
+pack = ops.EdgePairPack(lin, ln)
+e = torch.randn(n * k, 128, device=dev)
+P_r = torch.randn(n, 128, device=dev)
+P_c = torch.randn(n, 128, device=dev)
+topo = ops.MpTopo.from_edge_index(torch.stack([row, col]), n)
+e_out = torch.empty_like(e)
+agg = torch.empty(n, 128, device=dev)
+
+
+def launch():
+    ops.edge_aggr(pack, topo, e, P_r, P_c, act_e="selu", want_e=not a.no_e, e_out=e_out, agg_out=agg)
+
+
+for _ in range(3):
+    launch()
+torch.cuda.synchronize()
+ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+ev0.record()
+for _ in range(a.reps):
+    launch()
+ev1.record()
+torch.cuda.synchronize()
+ms = ev0.elapsed_time(ev1) / a.reps
+E = n * k
+alg = 4 * 128 * ((1 if a.no_e else 2) * E + 3 * n) + 4 * E
+flop = 2 * E * 128 * 128 * a.layers
+print(f"edge_pair_kernel: N={n} E={E} layers={a.layers} write_e={not a.no_e}: {ms:.3f} ms/launch, "
+      f"{alg / ms / 1e6:.1f} GB/s algorithmic ({alg / 1e9:.2f} GB), {flop / ms / 1e9:.1f} TFLOP/s useful "
+      f"({3 * flop / ms / 1e9:.1f} issued fp16)")
