@@ -16,11 +16,13 @@
 //   warps 0-7   epilogue: thread (row, half) owns 64 columns of its row.  TMEM -> registers, bias, SELU,
 //               fp16 (hi, lo) split written back to TMEM as the next layer's A operand (tcgen05.st); last
 //               layer: LayerNorm, aggregation, activation, 256-bit stores of e'.
-//   warps 8-11  loaders: coalesced 512-byte row reads of e, P_r[src], P_c[tgt]; e is split into fp16 (hi, lo)
-//               operand images, P_r + P_c (pre-scaled) into fp32 images; tcgen05.cp then moves the images
-//               into TMEM (A operand / initial accumulator), transposing "warp reads a row" into "lane owns
-//               a row" in hardware.
-//   warp 12     (leader CTA) issues every tcgen05.cp / tcgen05.mma of the pair; M = 256, N = 128, the B
+//   warps 8-11  loaders, one per TMEM lane quarter (32 tile rows each).  Rows of e, P_r[src], P_c[tgt] are
+//               fetched with cp.async (16 B per lane, whole 128-byte row pieces, no registers held across the
+//               HBM/L2 latency) into a private two-stage ring of 32-column stages; row pieces are stored at a
+//               144-byte pitch so that "lane = row" 16-byte reads are bank-conflict free.  The warp then reads
+//               its rows back with lane = row, splits e into fp16 (hi, lo) and writes it with tcgen05.st as the
+//               layer-1 A operand, and writes (P_r + P_c) * s as the INITIAL VALUE of the accumulator.
+//   warp 12     (leader CTA) issues every tcgen05.mma of the pair; M = 256, N = 128, the B
 //               operand (weights) is resident in shared memory, each CTA holding 64 of the 128 output rows
 //               of all layers as pre-split, pre-swizzled fp16 (hi, lo) images (96 KiB).
 // Two chains (even / odd slots) alternate so that the MMAs of one overlap the epilogue of the other.
@@ -34,18 +36,22 @@ namespace ep {
 using namespace tc2;
 using namespace pairk;
 
+constexpr int PITCH = 144;               // bytes between staged 128-byte row pieces (36 words: lanes r..r+7 hit 8 distinct 16 B bank groups)
+constexpr int ARR = 32 * PITCH;          // one array's 32 row pieces of a stage
+constexpr int STG = 3 * ARR;             // stage = e | P_r | P_c pieces of the warp's 32 rows, 32 columns
+constexpr int NSTG = 2;
+
 struct Smem {
     uint8_t w[3][4 * HIMG];          // layer l: K-block 0 hi | lo, K-block 1 hi | lo (64-row images)
-    uint8_t img_e[4][IMG];           // hi k0..63, hi k64..127, lo k0..63, lo k64..127
-    uint8_t img_p[4][IMG];           // fp32 columns 32q .. 32q+31
+    uint8_t ring[4][NSTG][STG];      // per loader warp
     float part[2][2][128];           // LayerNorm partial sums [pass][half][row]
     uint64_t w_full;
-    uint64_t in_full, in_empty;      // in_full: leader, 8 loader warps of the pair; in_empty: local, multicast commit
-    uint64_t a_ready[2], d_free[2];  // leader, 16 epilogue warps of the pair
+    uint64_t in_ready[2];            // leader: A operand + initial accumulator of chain c written (8 loader warps of the pair)
+    uint64_t a_ready[2];             // leader: next layer's A operand written (16 epilogue warps of the pair)
+    uint64_t d_free[2];              // local: accumulator of chain c has been read by the last-layer epilogue (8 warps)
     uint64_t d_full[2];              // local, multicast commit
     uint32_t tmem_base;
 };
-
 static_assert(sizeof(Smem) <= 232448, "edge kernel shared memory exceeds the 227 KiB opt-in limit");
 
 // largest in-degree over the (up to) 256 targets of unit pair `up`; executed by a full warp
@@ -89,11 +95,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_pair_ker
 
     if (tid == 0) {
         mbar_init(&s.w_full, 1);
-        mbar_init(&s.in_full, 8);
-        mbar_init(&s.in_empty, 1);
         for (int c = 0; c < 2; ++c) {
+            mbar_init(&s.in_ready[c], 8);
             mbar_init(&s.a_ready[c], 16);
-            mbar_init(&s.d_free[c], 16);
+            mbar_init(&s.d_free[c], 8);
             mbar_init(&s.d_full[c], 1);
         }
         fence_barrier_init();
@@ -107,7 +112,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_pair_ker
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem = s.tmem_base;
-    const uint32_t leader_in_full = mapa(smem_u32(&s.in_full), 0);
 
     if (warp < 8) {
         // ====================================================================== epilogue warps
@@ -115,7 +119,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_pair_ker
         const int row = (warp & 3) * 32 + lane, half = warp >> 2;
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         const uint32_t leader_a_ready[2] = {mapa(smem_u32(&s.a_ready[0]), 0), mapa(smem_u32(&s.a_ready[1]), 0)};
-        const uint32_t leader_d_free[2] = {mapa(smem_u32(&s.d_free[0]), 0), mapa(smem_u32(&s.d_free[1]), 0)};
         uint32_t n_dfull[2] = {0, 0};
         const float* gamma = a.gamma ? a.gamma + half * 64 : nullptr;
         const float* beta = a.beta ? a.beta + half * 64 : nullptr;
@@ -162,7 +165,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_pair_ker
                             }
                             tc_fence_before();
                             __syncwarp();
-                            if (lane == 0) mbar_arrive_cluster(leader_d_free[c]);
+                            if (lane == 0) mbar_arrive(&s.d_free[c]);
                             if (gamma) {
                                 float sum = 0.f;
 #pragma unroll
@@ -228,65 +231,126 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_pair_ker
         setmaxnreg_dec<kRegsLoad>();
         const int lw = warp - 8;
         const float ps = a.p_scale;
-        uint32_t g = 0;
-        mbar_wait(&s.w_full, 0);           // in_full is only signalled once this CTA's weights have landed
+        const uint32_t lane_base = (uint32_t)(lw * 32) << 16;
+        const uint32_t ring0 = smem_u32(s.ring[lw][0]);
+        const uint32_t leader_in_ready[2] = {mapa(smem_u32(&s.in_ready[0]), 0), mapa(smem_u32(&s.in_ready[1]), 0)};
+        const int64_t row_in_pair = (int64_t)rank * 128 + lw * 32 + lane;
+        mbar_wait(&s.w_full, 0);           // in_ready is only signalled once this CTA's weights have landed
+
+        // issue cursor (runs one stage ahead of the processing cursor); lane = tile row
+        int64_t i_up = up0;
+        int i_j = 0, i_cs = 0, i_maxdeg = 0, i_erow = -1, i_srow = -1, nx_erow = -1, nx_srow = -1;
+        RowMeta i_rm{0, 0, -1};
+        bool i_live = false;
+        auto issue_seek_unit = [&]() {        // position on the first slot of the first non-empty unit at or after i_up
+            i_live = false;
+            while (i_up < n_up) {
+                i_maxdeg = pair_maxdeg(a, i_up, lane);
+                if (i_maxdeg > 0) { i_live = true; break; }
+                i_up += up_stride;
+            }
+            if (i_live) { i_rm = row_meta(a, i_up * 256 + row_in_pair); i_j = 0; i_cs = 0; }
+        };
+        auto load_idx = [&](int j, int& erow, int& srow) {      // storage row of the j-th in-edge of this lane's target, its source
+            erow = -1; srow = -1;
+            if (i_rm.trow >= 0 && j < i_rm.deg) {
+                const int slot = i_rm.base + j;
+                erow = a.edge_perm ? __ldg(a.edge_perm + slot) : slot;
+                srow = __ldg(a.src + slot);
+            }
+        };
+        auto issue_load_idx = [&]() { load_idx(i_j, i_erow, i_srow); };
+        auto issue_stage = [&](uint32_t stage_addr) {     // cp.async the 32-column stage (i_up, i_j, i_cs) of this warp's rows
+            const int sub = lane >> 3, piece = lane & 7;   // 4 rows per instruction, 8 x 16 B per row piece
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int rr = 4 * i + sub;
+                const int er = __shfl_sync(0xffffffffu, i_erow, rr);
+                const int sr = __shfl_sync(0xffffffffu, i_srow, rr);
+                const int tr = __shfl_sync(0xffffffffu, i_rm.trow, rr);
+                const bool ok = er >= 0;
+                const uint32_t dst = stage_addr + (uint32_t)rr * PITCH + piece * 16;
+                const size_t col = (size_t)i_cs * 32 + piece * 4;
+                cp_async16_zfill(dst, a.e_in + (ok ? (size_t)er * H : 0) + col, ok);
+                cp_async16_zfill(dst + ARR, a.P_r + (ok ? (size_t)sr * H : 0) + col, ok);
+                cp_async16_zfill(dst + 2 * ARR, a.P_c + (ok ? (size_t)tr * H : 0) + col, ok);
+            }
+            cp_async_commit();
+        };
+        auto issue_advance = [&]() {          // next stage in execution order
+            if (++i_cs < 4) {
+                if (i_cs == 1) load_idx(i_j + 1, nx_erow, nx_srow);     // indices of the next slot: three stages of slack
+                return;
+            }
+            i_cs = 0;
+            if (++i_j < i_maxdeg) { i_erow = nx_erow; i_srow = nx_srow; return; }
+            i_up += up_stride;
+            issue_seek_unit();
+            if (i_live) issue_load_idx();
+        };
+
+        issue_seek_unit();
+        if (i_live) { issue_load_idx(); issue_stage(ring0); issue_advance(); }
+        uint32_t q = 0, n_slot[2] = {0, 0};
         for (int64_t up = up0; up < n_up; up += up_stride) {
             const int maxdeg = pair_maxdeg(a, up, lane);
-            const RowMeta rm = row_meta(a, (up * 2 + rank) * 128 + lw * 32 + lane);
-            for (int j = 0; j < maxdeg; ++j, ++g) {
-                int erow = -1, srow = -1;
-                if (rm.trow >= 0 && j < rm.deg) {
-                    const int slot = rm.base + j;
-                    erow = a.edge_perm ? a.edge_perm[slot] : slot;
-                    srow = a.src[slot];
-                }
-                mbar_wait(&s.in_empty, (g + 1) & 1);
-#pragma unroll 1
-                for (int i0 = 0; i0 < 32; i0 += 4) {
-                    float4 xe[4], xr[4], xc[4];
-                    int er[4];
+            for (int j = 0; j < maxdeg; ++j) {
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        er[u] = __shfl_sync(0xffffffffu, erow, i0 + u);
-                        const int sr = __shfl_sync(0xffffffffu, srow, i0 + u);
-                        const int tr = __shfl_sync(0xffffffffu, rm.trow, i0 + u);
-                        xe[u] = xr[u] = xc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (er[u] >= 0) {
-                            xe[u] = ldg_stream(a.e_in + (size_t)er[u] * H + lane * 4);
-                            xr[u] = __ldg(reinterpret_cast<const float4*>(a.P_r + (size_t)sr * H + lane * 4));
-                            xc[u] = __ldg(reinterpret_cast<const float4*>(a.P_c + (size_t)tr * H + lane * 4));
+                for (int cc = 0; cc < 2; ++cc) {
+                    if ((j & 1) != cc) continue;
+                    const uint32_t d_col = tmem + lane_base + 256u * cc;
+#pragma unroll 1
+                    for (int cs = 0; cs < 4; ++cs, ++q) {
+                        // prefetch the next stage, then wait for this one
+                        if (i_live) { issue_stage(ring0 + ((q + 1) & 1) * STG); issue_advance(); cp_async_wait<1>(); }
+                        else cp_async_wait<0>();
+                        __syncwarp();
+                        if (cs == 0) {
+                            mbar_wait(&s.d_free[cc], (n_slot[cc] + 1) & 1);      // last-layer epilogue of the previous slot on this chain
+                            tc_fence_after();
+                        }
+                        const uint8_t* st = s.ring[lw][q & 1] + lane * PITCH;
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) {                          // 16 columns at a time
+                            uint32_t eh[8], el[8], pp[16];
+#pragma unroll
+                            for (int v4 = 0; v4 < 4; ++v4) {
+                                const float4 xe = *reinterpret_cast<const float4*>(st + hh * 64 + v4 * 16);
+                                const float4 xr = *reinterpret_cast<const float4*>(st + ARR + hh * 64 + v4 * 16);
+                                const float4 xc = *reinterpret_cast<const float4*>(st + 2 * ARR + hh * 64 + v4 * 16);
+                                split2(xe.x, xe.y, eh[2 * v4], el[2 * v4]);
+                                split2(xe.z, xe.w, eh[2 * v4 + 1], el[2 * v4 + 1]);
+                                pp[4 * v4] = __float_as_uint((xr.x + xc.x) * ps);
+                                pp[4 * v4 + 1] = __float_as_uint((xr.y + xc.y) * ps);
+                                pp[4 * v4 + 2] = __float_as_uint((xr.z + xc.z) * ps);
+                                pp[4 * v4 + 3] = __float_as_uint((xr.w + xc.w) * ps);
+                            }
+                            tmem_st8(d_col + 128u + 16u * cs + 8u * hh, eh);       // A hi: k = 32 cs + 16 hh .. +15
+                            tmem_st8(d_col + 192u + 16u * cs + 8u * hh, el);       // A lo
+                            tmem_st16(d_col + 32u * cs + 16u * hh, pp);            // accumulator columns 32 cs + 16 hh .. +15
+                        }
+                        if (cs == 3) {
+                            tmem_wait_st();
+                            tc_fence_before();
+                        }
+                        __syncwarp();                                             // stage buffer may be refilled
+                        if (cs == 3) {
+                            if (lane == 0) mbar_arrive_cluster(leader_in_ready[cc]);
+                            ++n_slot[cc];
                         }
                     }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int r = lw * 32 + i0 + u;
-                        uint2 h, l;
-                        split2(xe[u].x, xe[u].y, h.x, l.x);
-                        split2(xe[u].z, xe[u].w, h.y, l.y);
-                        const uint32_t off = (uint32_t)(lane >> 4) * IMG + img_off(r, (lane & 15) >> 1) + (lane & 1) * 8;
-                        *reinterpret_cast<uint2*>(s.img_e[0] + off) = h;
-                        *reinterpret_cast<uint2*>(s.img_e[2] + off) = l;
-                        const float4 p = make_float4((xr[u].x + xc[u].x) * ps, (xr[u].y + xc[u].y) * ps,
-                                                     (xr[u].z + xc[u].z) * ps, (xr[u].w + xc[u].w) * ps);
-                        *reinterpret_cast<float4*>(s.img_p[0] + (uint32_t)(lane >> 3) * IMG + img_off(r, lane & 7)) = p;
-                    }
                 }
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(leader_in_full);
             }
         }
     } else {
         setmaxnreg_dec<kRegsMisc>();
         if (warp == 12 && rank == 0) {
             // ================================================================== MMA / copy issuer (leader CTA)
-            // both CTAs' weights are in place once in_full completes (every loader warp waited on its w_full)
+            // both CTAs' weights are in place once in_ready completes (every loader warp waited on its w_full)
             const uint32_t idesc = idesc_f16(256, 128);
             // descriptors differ only in their 14-bit start-address field (byte address >> 4): add offsets to a base
             const uint64_t w_desc = make_desc_sw128(smem_u32(s.w[0]));
-            const uint64_t e_desc = make_desc_sw128(smem_u32(s.img_e[0]));
-            const uint64_t p_desc = make_desc_sw128(smem_u32(s.img_p[0]));
-            uint32_t g = 0, n_chain[2] = {0, 0}, n_ar[2] = {0, 0};
+            uint32_t n_chain[2] = {0, 0}, n_ar[2] = {0, 0};
             for (int64_t up = up0; up < n_up; up += up_stride) {
                 const int maxdeg = pair_maxdeg(a, up, lane);
                 for (int j0 = 0; j0 < maxdeg; j0 += 2) {
@@ -298,21 +362,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_pair_ker
                             const uint32_t d_col = tmem + 256u * c, ah = d_col + 128u, al = d_col + 192u;
                             if (l == 0) {
                                 if (lane == 0) {
-                                    mbar_wait<true>(&s.d_free[c], (n_chain[c] + 1) & 1);
-                                    mbar_wait<true>(&s.in_full, g & 1);
+                                    mbar_wait<true>(&s.in_ready[c], n_chain[c] & 1);
                                     tc_fence_after();
-#pragma unroll 1
-                                    for (int i = 0; i < 16; ++i)          // P_r[src] + P_c[tgt] -> accumulator (fp32, 8 columns per copy)
-                                        tmem_cp_128x256b<2>(d_col + 8 * i, p_desc + (uint64_t)(((i >> 2) * IMG + (i & 3) * 32) >> 4));
-#pragma unroll 1
-                                    for (int i = 0; i < 8; ++i) {         // e (hi, lo) -> A operand (16 k per copy)
-                                        const uint64_t off = (uint64_t)(((i >> 2) * IMG + (i & 3) * 32) >> 4);
-                                        tmem_cp_128x256b<2>(ah + 8 * i, e_desc + off);
-                                        tmem_cp_128x256b<2>(al + 8 * i, e_desc + off + (uint64_t)((2 * IMG) >> 4));
-                                    }
-                                    umma_commit<2>(&s.in_empty, 3);
                                 }
-                                ++g;
                                 ++n_chain[c];
                             } else {
                                 if (lane == 0) {

@@ -65,6 +65,7 @@ class Rollout:
         self.H = hidden_width(self.params)
         self.prog = block_program(self.params)
         self.packs = {}
+        self._ws = {}
         self.use_graph = cuda_graph
         self._graph = None
         self.launches_per_step = 0
@@ -197,14 +198,35 @@ class Rollout:
         self.launches_per_step = len(steps) + 1      # + step_update
 
     # ------------------------------------------------------------------ execution
+    def _row_precision(self, pack, segs, residual):
+        """fp16x3 runs every row MLP the tensor-core kernel supports on it; the rest stays on the fp32 kernel."""
+        if self.precision != "fp16x3":
+            return "fp32"
+        widths = [int(t.shape[1]) for t, _, _ in segs]
+        ok = pack.tc_row_ok(widths) and not (residual is not None and pack.out_width == 128)
+        return "fp16x3" if ok else "fp32"
+
+    def _mp_workspace(self, n_src, n_tgt):
+        """(P_r, P_c, agg) of the tensor-core message-passing path, shared by every block of the same size."""
+        if self.precision != "fp16x3":
+            return None
+        ws = self._ws.get((n_src, n_tgt))
+        if ws is None:
+            mk = lambda n: torch.empty(n, 128, device=self.device, dtype=torch.float32)
+            ws = self._ws[(n_src, n_tgt)] = (mk(n_src), mk(n_tgt), mk(n_tgt))
+        return ws
+
     def _run_step_eager(self):
         for op, a in self.steps:
             if op == "rowmlp":
-                ops.rowmlp(a["pack"], a["segs"], rows=a.get("rows"), act=a["act"], out=a["out"], residual=a.get("residual"))
+                ops.rowmlp(a["pack"], a["segs"], rows=a.get("rows"), act=a["act"], out=a["out"], residual=a.get("residual"),
+                           precision=self._row_precision(a["pack"], a["segs"], a.get("residual")))
             elif op == "mp":
-                ops.mp(a["ep"], a["np_"], a["topo"], a["e_in"], a.get("s_in", a["v_in"]), a["v_in"],
+                s_in = a.get("s_in", a["v_in"])
+                ops.mp(a["ep"], a["np_"], a["topo"], a["e_in"], s_in, a["v_in"],
                        aggr=a.get("aggr", "mean"), act_e=a.get("act_e", "selu"), act_t=a.get("act_t", "selu"),
-                       want_e=a["e_out"] is not None, precision=self.precision, e_out=a["e_out"], t_out=a["v_out"])
+                       want_e=a["e_out"] is not None, precision=self.precision, e_out=a["e_out"], t_out=a["v_out"],
+                       ws=self._mp_workspace(int(s_in.shape[0]), int(a["v_in"].shape[0])))
             elif op == "seg":
                 ops.seg_reduce(a["x"], a["ptr"], a["idx"], a["n"], "mean", a["act"], out=a["out"])
             elif op == "call":
@@ -221,7 +243,9 @@ class Rollout:
             s = torch.cuda.Stream(device=self.device)
             s.wait_stream(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(s):
+                n0 = ops.L.launch_count()
                 self._run_step_eager()
+                self.launches_per_step = ops.L.launch_count() - n0 + 1      # + step_update
             torch.cuda.current_stream(self.device).wait_stream(s)
             torch.cuda.synchronize(self.device)
             self._graph = torch.cuda.CUDAGraph()
