@@ -207,6 +207,12 @@ int g4c_debug_tc2(int32_t test, const float* A, const void* W_pack, float w_inv_
     return tc2_test_launch(test, A, W_pack, w_inv_scale, P, D, flags, static_cast<cudaStream_t>(stream));
 }
 
+int g4c_debug_profile(uint64_t* out64) {
+    if (!out64) { set_error("g4c_debug_profile: NULL pointer"); return G4C_EINVAL; }
+    cudaDeviceSynchronize();
+    return edge_pair_profile(reinterpret_cast<unsigned long long*>(out64));
+}
+
 int g4c_host_guillard(const int64_t* senders, int64_t n, int32_t k, uint8_t* coarse_mask) {
     if (!senders || !coarse_mask || n < 0 || k < 1) { set_error("g4c_host_guillard: bad arguments"); return G4C_EINVAL; }
     memset(coarse_mask, 1, (size_t)n);

@@ -52,6 +52,21 @@ struct Smem {
     uint64_t d_full[2];              // local, multicast commit
     uint32_t tmem_base;
 };
+// ---- optional in-kernel phase profile (make EXTRA=-DG4C_PROFILE): cycles spent per role and phase by CTA 0,
+// accumulated by lane 0 of each warp; read back with g4c_debug_profile().
+#ifdef G4C_PROFILE
+__device__ unsigned long long g_prof[64];
+#define PROF_DECL unsigned int prof_t0 = 0; unsigned long long prof_acc[6] = {0, 0, 0, 0, 0, 0};
+#define PROF_START() prof_t0 = clock()
+#define PROF_LAP(i) do { const unsigned int t1 = clock(); prof_acc[i] += (unsigned int)(t1 - prof_t0); prof_t0 = t1; } while (0)
+#define PROF_FLUSH(base) do { if (blockIdx.x == 0 && lane == 0) for (int i = 0; i < 6; ++i) atomicAdd(&g_prof[(base) + i], prof_acc[i]); } while (0)
+#else
+#define PROF_DECL
+#define PROF_START()
+#define PROF_LAP(i)
+#define PROF_FLUSH(base)
+#endif
+
 static_assert(sizeof(Smem) <= 232448, "edge kernel shared memory exceeds the 227 KiB opt-in limit");
 
 // largest in-degree over the (up to) 256 targets of unit pair `up`; executed by a full warp
@@ -120,6 +135,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_pair_ker
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         const uint32_t leader_a_ready[2] = {mapa(smem_u32(&s.a_ready[0]), 0), mapa(smem_u32(&s.a_ready[1]), 0)};
         uint32_t n_dfull[2] = {0, 0};
+        PROF_DECL
+        PROF_START();
         const float* gamma = a.gamma ? a.gamma + half * 64 : nullptr;
         const float* beta = a.beta ? a.beta + half * 64 : nullptr;
 
@@ -140,6 +157,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_pair_ker
                         mbar_wait(&s.d_full[c], n_dfull[c] & 1);
                         ++n_dfull[c];
                         tc_fence_after();
+                        PROF_LAP(0);                     // waiting for MMA completion
                         if (l < nl - 1) {
                             epilogue_hidden(d_addr, tmem + lane_base + 256u * c + 128u + 32u * half,
                                             tmem + lane_base + 256u * c + 192u + 32u * half, a.inv_scale[l],
@@ -147,6 +165,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_pair_ker
                             tc_fence_before();
                             __syncwarp();
                             if (lane == 0) mbar_arrive_cluster(leader_a_ready[c]);
+                            PROF_LAP(1);                 // hidden epilogue
                         } else {
                             // ---- last layer: LayerNorm, aggregation, store
                             float y[64];
@@ -166,6 +185,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_pair_ker
                             tc_fence_before();
                             __syncwarp();
                             if (lane == 0) mbar_arrive(&s.d_free[c]);
+                            PROF_LAP(2);                 // last epilogue up to the release of the accumulator
                             if (gamma) {
                                 float sum = 0.f;
 #pragma unroll
@@ -209,6 +229,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_pair_ker
                                     }
                                 }
                             }
+                            PROF_LAP(3);                 // LayerNorm, aggregation, stores
                         }
                     }
                 }
@@ -225,7 +246,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_pair_ker
                     stg256(dst + i, o);
                 }
             }
+            PROF_LAP(4);
         }
+        PROF_FLUSH(warp < 4 ? 0 : 8);
     } else if (warp < 12) {
         // ====================================================================== loader warps
         setmaxnreg_dec<kRegsLoad>();
@@ -292,6 +315,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_pair_ker
         issue_seek_unit();
         if (i_live) { issue_load_idx(); issue_stage(ring0); issue_advance(); }
         uint32_t q = 0, n_slot[2] = {0, 0};
+        PROF_DECL
+        PROF_START();
         for (int64_t up = up0; up < n_up; up += up_stride) {
             const int maxdeg = pair_maxdeg(a, up, lane);
             for (int j = 0; j < maxdeg; ++j) {
@@ -302,12 +327,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_pair_ker
 #pragma unroll 1
                     for (int cs = 0; cs < 4; ++cs, ++q) {
                         // prefetch the next stage, then wait for this one
-                        if (i_live) { issue_stage(ring0 + ((q + 1) & 1) * STG); issue_advance(); cp_async_wait<1>(); }
+                        if (i_live) { issue_stage(ring0 + ((q + 1) & 1) * STG); issue_advance(); PROF_LAP(0); cp_async_wait<1>(); }
                         else cp_async_wait<0>();
                         __syncwarp();
+                        PROF_LAP(1);                     // waiting for the staged rows
                         if (cs == 0) {
                             mbar_wait(&s.d_free[cc], (n_slot[cc] + 1) & 1);      // last-layer epilogue of the previous slot on this chain
                             tc_fence_after();
+                            PROF_LAP(2);                 // waiting for the accumulator to be released
                         }
                         const uint8_t* st = s.ring[lw][q & 1] + lane * PITCH;
 #pragma unroll
@@ -338,10 +365,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_pair_ker
                             if (lane == 0) mbar_arrive_cluster(leader_in_ready[cc]);
                             ++n_slot[cc];
                         }
+                        PROF_LAP(3);                     // split / add / TMEM writes
                     }
                 }
             }
         }
+        PROF_FLUSH(16);
     } else {
         setmaxnreg_dec<kRegsMisc>();
         if (warp == 12 && rank == 0) {
@@ -351,6 +380,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_pair_ker
             // descriptors differ only in their 14-bit start-address field (byte address >> 4): add offsets to a base
             const uint64_t w_desc = make_desc_sw128(smem_u32(s.w[0]));
             uint32_t n_chain[2] = {0, 0}, n_ar[2] = {0, 0};
+            PROF_DECL
+            PROF_START();
             for (int64_t up = up0; up < n_up; up += up_stride) {
                 const int maxdeg = pair_maxdeg(a, up, lane);
                 for (int j0 = 0; j0 < maxdeg; j0 += 2) {
@@ -364,12 +395,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_pair_ker
                                 if (lane == 0) {
                                     mbar_wait<true>(&s.in_ready[c], n_chain[c] & 1);
                                     tc_fence_after();
+                                    PROF_LAP(0);         // waiting for the loaders
                                 }
                                 ++n_chain[c];
                             } else {
                                 if (lane == 0) {
                                     mbar_wait<true>(&s.a_ready[c], n_ar[c] & 1);
                                     tc_fence_after();
+                                    PROF_LAP(1);         // waiting for the epilogue
                                 }
                                 ++n_ar[c];
                             }
@@ -384,12 +417,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_pair_ker
                                     umma_ts<2>(d_col, ah + 8 * ks, wl, idesc, 1u);
                                 }
                                 umma_commit<2>(&s.d_full[c], 3);
+                                PROF_LAP(2);             // issuing
                             }
                             __syncwarp();
                         }
                     }
                 }
             }
+            PROF_FLUSH(24);
         }
     }
 
@@ -399,6 +434,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_pair_ker
 }
 
 }  // namespace ep
+
+int edge_pair_profile(unsigned long long* out64) {
+#ifdef G4C_PROFILE
+    if (cudaMemcpyFromSymbol(out64, ep::g_prof, sizeof(unsigned long long) * 64) != cudaSuccess) return check_launch("profile read");
+    unsigned long long zero[64] = {0};
+    cudaMemcpyToSymbol(ep::g_prof, zero, sizeof(zero));
+    return G4C_OK;
+#else
+    (void)out64;
+    set_error("libg4c was built without -DG4C_PROFILE");
+    return G4C_EUNSUPPORTED;
+#endif
+}
 
 int edge_pair_launch(const EdgeArgs& a, cudaStream_t st) {
     static bool configured = false;

@@ -287,6 +287,9 @@ G4C_API int g4c_debug_tc_gemm(const float* A, const void* W_pack, float w_inv_sc
 G4C_API int g4c_debug_tc2(int32_t test, const float* A, const void* W_pack, float w_inv_scale, const float* P, float* D,
                           int32_t flags, void* stream);
 
+/* in-kernel phase profile of edge_pair_kernel (HOST pointer to 64 uint64; only in builds with -DG4C_PROFILE) */
+G4C_API int g4c_debug_profile(uint64_t* out64);
+
 G4C_API int g4c_host_guillard(const int64_t* senders, int64_t n, int32_t k, uint8_t* coarse_mask);
 
 #ifdef __cplusplus

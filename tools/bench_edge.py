@@ -56,3 +56,21 @@ flop = 2 * E * 128 * 128 * a.layers
 print(f"edge_pair_kernel: N={n} E={E} layers={a.layers} write_e={not a.no_e}: {ms:.3f} ms/launch, "
       f"{alg / ms / 1e6:.1f} GB/s algorithmic ({alg / 1e9:.2f} GB), {flop / ms / 1e9:.1f} TFLOP/s useful "
       f"({3 * flop / ms / 1e9:.1f} issued fp16)")
+
+if os.environ.get("G4C_PROFILE"):
+    import ctypes as C
+    import numpy as np
+    from graphs4cfd_b200 import _lib as L
+    buf = np.zeros(64, dtype=np.uint64)
+    L.lib().g4c_debug_profile(buf.ctypes.data_as(C.c_void_p))        # drop warm-up + timing launches
+    launch()
+    L.check(L.lib().g4c_debug_profile(buf.ctypes.data_as(C.c_void_p)))
+    names = {0: ("epilogue warps 0-3 (sum of 4)", ["wait MMA", "hidden epi", "last epi: acc read", "LN+agg+store", "unit end", "-"]),
+             8: ("epilogue warps 4-7 (sum of 4)", ["wait MMA", "hidden epi", "last epi: acc read", "LN+agg+store", "unit end", "-"]),
+             16: ("loader warps (sum of 4)", ["issue cp.async", "wait rows", "wait acc release", "process+TMEM st", "-", "-"]),
+             24: ("MMA issuer", ["wait loaders", "wait epilogue", "issue", "-", "-", "-"])}
+    for base, (who, labels) in names.items():
+        vals = buf[base:base + 6].astype(np.float64)
+        nw = 1 if base == 24 else 4
+        tot = vals.sum()
+        print(f"{who}: total {tot / nw / 1e6:.3f} Mcycles per warp; " + ", ".join(f"{l} {100 * v / tot:.1f}%" for l, v in zip(labels, vals) if l != "-"))
