@@ -8,7 +8,7 @@ import numpy as np
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libg4c.so")
+LIB_PATH = os.environ.get("G4C_LIB", os.path.join(_HERE, "libg4c.so"))      # G4C_LIB: alternative build (e.g. the -DG4C_PROFILE one)
 
 ACT_NONE, ACT_SELU, ACT_TANH = 0, 1, 2
 AGGR_MEAN, AGGR_SUM = 0, 1

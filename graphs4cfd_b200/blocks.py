@@ -13,6 +13,7 @@ Two ways in:
 Inputs must be contiguous fp32 CUDA tensors; anything else raises (no CPU / eager fallback).
 Autograd is not supported (inference path): calling a block with grad-requiring inputs raises.
 """
+import weakref
 from collections import OrderedDict
 from typing import Callable, Optional, Tuple
 
@@ -44,22 +45,41 @@ def _no_grad_guard(*tensors):
 
 
 class _Cache:
-    """Per-module cache of static plans keyed by the identity of the index tensors."""
+    """Per-process cache of static plans keyed by the identity of the index tensors.  An entry keeps weak
+    references to its key tensors and is only valid while they are alive: the caching allocator may hand the
+    address of a freed index tensor to a new one with different contents."""
 
     def __init__(self):
         self._d = {}
 
     @staticmethod
     def key(*tensors):
-        return tuple((t.data_ptr(), tuple(t.shape), t._version) for t in tensors)
+        return _Key(tensors)
 
     def get(self, key, build):
-        hit = self._d.get(key)
-        if hit is None:
-            if len(self._d) > 16:
-                self._d.clear()
-            hit = self._d[key] = build()
-        return hit
+        tensors = tuple(t for part in key if isinstance(part, _Key) for t in part.tensors)
+        flat = tuple(part.ident if isinstance(part, _Key) else part for part in key)
+        hit = self._d.get(flat)
+        if hit is not None and all(r() is not None for r in hit[0]):
+            return hit[1]
+        if len(self._d) > 16:
+            self._d.clear()
+        value = build()
+        self._d[flat] = (tuple(weakref.ref(t) for t in tensors), value)
+        return value
+
+
+class _Key(tuple):
+    """(data_ptr, shape, version) of each tensor, remembering the tensors themselves for the liveness check."""
+
+    def __new__(cls, tensors):
+        self = super().__new__(cls, ())
+        self.tensors = tuple(tensors)
+        self.ident = tuple((t.data_ptr(), tuple(t.shape), t._version) for t in tensors)
+        return self
+
+    def __radd__(self, other):
+        return tuple(other) + (self,)
 
 
 _TOPO_CACHE = _Cache()

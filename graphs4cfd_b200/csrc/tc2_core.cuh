@@ -29,7 +29,7 @@ using tc::tc_fence_before;
 using tc::tmem_ld32;
 using tc::bulk_g2s;
 
-constexpr uint32_t kWatchdogSpins = 1u << 22;
+constexpr uint32_t kWatchdogSpins = 1u << 24;
 
 // kind::f16 instruction descriptor: D=f32, A=B=f16, both K-major
 __host__ __device__ constexpr uint32_t idesc_f16(uint32_t M, uint32_t N) {
@@ -51,27 +51,27 @@ __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t cta) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
     return r;
 }
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+// arrive on an mbarrier of another CTA of the cluster (address from mapa).  Default semantics (.release.cta), the
+// form CUTLASS uses for 2-CTA pipelines: the data handed over lives in TMEM and is ordered by
+// tcgen05.wait::st + tcgen05.fence::before_thread_sync, so no MEMBAR.ALL.GPU (which the .release.cluster form
+// emits, and which would also wait for every global store of the thread) is needed.
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) { mbar_arrive_remote(cluster_addr); }
 
 // ------------------------------------------------------------------ bounded waits
+// plain (cta-scope acquire) try_wait: the data handed over through these barriers lives in TMEM or was written by
+// the async proxy, and is ordered by tcgen05 fences / complete_tx; a .acquire.cluster wait would add a CCTL.IVALL
+// (L1 invalidation) to every successful wait.
 template <bool kClusterScope>
 __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
-    if (kClusterScope) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}\n"
-            : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    } else {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}\n"
-            : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    }
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
 template <bool kClusterScope = false>
@@ -80,6 +80,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try<kClusterScope>(bar, parity)) {
         if (++spins > kWatchdogSpins) __trap();
     }
+}
+
+// Waiting without taking issue slots from the working warps of the same scheduler: try_wait with a suspend-time
+// hint compiles to TRYWAIT + NANOSLEEP.SYNCS (the warp sleeps until mbarrier activity or the hint expires).  A plain
+// try_wait loop re-issues every ~20 cycles, which with several waiting warps per scheduler starves the others.
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0, ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
+        if (!ok && ++spins > kWatchdogSpins) __trap();
+    } while (!ok);
 }
 
 // ------------------------------------------------------------------ TMEM management
@@ -162,6 +177,9 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
                  "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                  : "memory");
 }
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&r)[4]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+}
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -191,6 +209,15 @@ __device__ __forceinline__ void tmem_ld32f(uint32_t taddr, float* v) {
         : "memory");
 }
 
+// 16 fp32 columns, no implicit wait (caller batches loads, then tmem_wait_ld())
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]),
+          "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld16f(uint32_t taddr, float* v) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n\t"

@@ -71,8 +71,9 @@ def test_edge_pair_fixed_k(n, k, n_layers):
 
 
 @gpu
+@pytest.mark.parametrize("n_layers", [3, 2])
 @pytest.mark.parametrize("aggr", ["mean", "sum"])
-def test_edge_pair_irregular(aggr):
+def test_edge_pair_irregular(aggr, n_layers):
     """Variable in-degree (0..9), edges in arbitrary storage order (edge_perm path), isolated targets."""
     dev = torch.device("cuda")
     g = torch.Generator().manual_seed(3)
@@ -82,7 +83,7 @@ def test_edge_pair_irregular(aggr):
     perm = torch.randperm(col.numel(), generator=g)
     col = col[perm].to(dev)
     row = torch.randint(0, n, (col.numel(),), generator=g).to(dev)
-    _run(n, row, col, 3, aggr, None)
+    _run(n, row, col, n_layers, aggr, None)
 
 
 @gpu

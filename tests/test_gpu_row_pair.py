@@ -60,6 +60,11 @@ def test_node_model(rows):
 
 
 @gpu
+def test_node_model_two_layers():
+    _check(1000, [128, 128], [128, 128], True, "selu")
+
+
+@gpu
 def test_two_layer_and_no_ln():
     _check(3001, [128], [128, 128], False, None)
 

@@ -65,12 +65,12 @@ if os.environ.get("G4C_PROFILE"):
     L.lib().g4c_debug_profile(buf.ctypes.data_as(C.c_void_p))        # drop warm-up + timing launches
     launch()
     L.check(L.lib().g4c_debug_profile(buf.ctypes.data_as(C.c_void_p)))
-    names = {0: ("epilogue warps 0-3 (sum of 4)", ["wait MMA", "hidden epi", "last epi: acc read", "LN+agg+store", "unit end", "-"]),
-             8: ("epilogue warps 4-7 (sum of 4)", ["wait MMA", "hidden epi", "last epi: acc read", "LN+agg+store", "unit end", "-"]),
-             16: ("loader warps (sum of 4)", ["issue cp.async", "wait rows", "wait acc release", "process+TMEM st", "-", "-"]),
-             24: ("MMA issuer", ["wait loaders", "wait epilogue", "issue", "-", "-", "-"])}
+    names = {0: ("epilogue warp 0", ["wait MMA (hidden)", "wait MMA (last)", "hidden epilogue", "last: statistics", "last: barrier", "last: normalise+agg+store", "unit end", "-"]),
+             8: ("loader warp 16", ["wait rows", "wait acc release", "process + prefetch", "-", "-", "-", "-", "-"]),
+             16: ("MMA issuer", ["wait loaders", "wait epilogue", "issue", "-", "-", "-", "-", "-"])}
+    n_slots = (n + 127) // 128 * k / 148.0
     for base, (who, labels) in names.items():
-        vals = buf[base:base + 6].astype(np.float64)
-        nw = 1 if base == 24 else 4
+        vals = buf[base:base + 8].astype(np.float64)
         tot = vals.sum()
-        print(f"{who}: total {tot / nw / 1e6:.3f} Mcycles per warp; " + ", ".join(f"{l} {100 * v / tot:.1f}%" for l, v in zip(labels, vals) if l != "-"))
+        print(f"{who}: total {tot / 1e6:.3f} Mcycles = {tot / n_slots:.0f} per slot; " +
+              ", ".join(f"{l} {100 * v / tot:.1f}% ({v / n_slots:.0f}/slot)" for l, v in zip(labels, vals) if l != "-"))
