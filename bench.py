@@ -34,7 +34,8 @@ def parse():
     ap.add_argument("--hidden", type=int, default=128)
     ap.add_argument("--k", type=int, default=6)
     ap.add_argument("--levels", type=int, default=3)
-    ap.add_argument("--precision", default=os.environ.get("G4C_PRECISION", "fp32"))
+    ap.add_argument("--precision", default=os.environ.get("G4C_PRECISION", "auto"),
+                    help="auto (fp16x3 tensor-core path when hidden=128, else fp32) | fp16x3 | fp32")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--cpu-sample-nodes", type=int, default=50_000)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
@@ -228,9 +229,9 @@ def run_g4c(a):
             cb, _ = cpu_steps_per_s(a, 2, 1, a.cpu_sample_nodes)
         line = {"metric": "rollout_steps_per_s", "value": a.steps / (ms * 1e-3), "unit": "steps/s", "n_gpus": world,
                 "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "f32" if a.precision == "fp32" else a.precision,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32" if eng.precision == "fp32" else eng.precision,
                 "data": "synthetic",
-                "config": {"workload": workload_name(a), "precision": a.precision,
+                "config": {"workload": workload_name(a), "precision": eng.precision,
                            "parallelism": f"node-range partition x{world}" if world > 1 else "single GPU",
                            "cuda_graph": not a.no_graph, "weights": "seeded default init",
                            "l2": "inputs larger than L2 (level-1 edge features %.1f GB per buffer)" % (a.nodes * a.k * a.hidden * 4 / 1e9)},
@@ -243,46 +244,86 @@ def run_g4c(a):
         dist.destroy_process_group()
 
 
-def roofline_mp(eng, a, dev, ms_per_step):
-    from graphs4cfd_b200 import ops
-    mp_steps = [s for s in eng.steps if s[0] == "mp"]
-    lvl1 = [s for s in mp_steps if s[1]["topo"].n_edges == mp_steps[0][1]["topo"].n_edges]
-    arg = next(s[1] for s in lvl1 if s[1]["e_out"] is not None)
-    topo = arg["topo"]
-    H = a.hidden
+def _peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback (B200_PROFILING.md)"
 
-    def launch():
-        ops.mp(arg["ep"], arg["np_"], topo, arg["e_in"], arg["v_in"], arg["v_in"], act_e="selu", act_t="selu",
-               want_e=True, precision=eng.precision, e_out=arg["e_out"], t_out=arg["v_out"])
 
-    for _ in range(2):
-        launch()
+def _time_launch(fn, dev, reps=10):
+    for _ in range(3):
+        fn()
     torch.cuda.synchronize(dev)
-    reps = 5
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
-        launch()
+        fn()
     e1.record()
     torch.cuda.synchronize(dev)
-    dur_ms = e0.elapsed_time(e1) / reps
+    return e0.elapsed_time(e1) / reps
+
+
+def roofline_mp(eng, a, dev, ms_per_step):
+    """Roofline of the dominant kernel, timed alone with CUDA events on the launching stream (torch's current
+    stream, which libg4c launches on): the level-1 fused edge-MLP + aggregation launch that keeps e'.
+    fp16x3: `edge_pair_kernel` (g4c_edge_aggr_fwd) on the engine's own buffers; fp32: the fused `mp_kernel`.
+    Inputs (3 GB of edge features per buffer at 1M nodes) are far larger than L2."""
+    from graphs4cfd_b200 import ops
+    mp_args = [s[1] for s in eng.steps if s[0] == "mp"] if hasattr(eng, "steps") else eng.mp_args   # single GPU / rank-local
+    lvl1 = [m for m in mp_args if m["topo"].n_edges == mp_args[0]["topo"].n_edges]
+    arg = next(m for m in lvl1 if m["e_out"] is not None)
+    topo = arg["topo"]
+    H = a.hidden
     E, N = topo.n_edges, topo.n_targets
-    alg_bytes = 4 * H * (2 * E + 2 * N) + 4 * E + (0 if topo.fixed_k else 4 * N)
-    flops = 2 * E * (3 * H * H + 2 * H * H) + 2 * N * (2 * H * H + 2 * H * H)
-    peaks, src = {}, "fallback"
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        src = "measured"
-    except Exception:
-        peaks = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
+    peaks, src = _peaks()
+    n_with_e = sum(1 for m in lvl1 if m["e_out"] is not None)
+    if eng.precision == "fp16x3":
+        ep, _, _ = arg["ep"].tc_edge()
+        n_rows = int(arg["v_in"].shape[0])                  # own + ghost rows on a partition
+        P_r, P_c, agg = (torch.empty(n_rows, 128, device=dev) for _ in range(3))
+
+        def launch():
+            ops.edge_aggr(ep, topo, arg["e_in"], P_r, P_c, act_e="selu", want_e=True, e_out=arg["e_out"], agg_out=agg)
+
+        def launch_mp():
+            ops.mp(arg["ep"], arg["np_"], topo, arg["e_in"], arg["v_in"], arg["v_in"], act_e="selu", act_t="selu",
+                   want_e=True, precision=eng.precision, e_out=arg["e_out"], t_out=arg["v_out"], ws=(P_r, P_c, agg))
+
+        dur_ms = _time_launch(launch, dev)
+        mp_ms = _time_launch(launch_mp, dev)
+        # each tensor touched once: read e, write e', read P_r, P_c, write agg (fp32 rows of H), read src ids (DESIGN.md 4.1)
+        alg_bytes = 4 * H * (2 * E + 3 * N) + 4 * E + (0 if topo.fixed_k else 4 * N)
+        flops = 2 * E * 3 * H * H                     # three K = H layers per edge (the gathered terms cost no MMA)
+        kernel = "edge_pair_kernel (g4c_edge_aggr_fwd: level-1 fused edge MLP + LayerNorm + aggregation, e' kept)"
+        extra = {"mp_block_ms": mp_ms, "mp_block_launches": 4,
+                 "tensor": {"issued_fp16_tflops": 3 * flops / (dur_ms * 1e-3) / 1e12, "peak_bf16_tflops": peaks.get("bf16_tflops"),
+                            "frac": 3 * flops / (dur_ms * 1e-3) / 1e12 / peaks.get("bf16_tflops", 1590.0),
+                            "note": "fp16x3: every product is issued as 3 fp16 MMAs with fp32 accumulation"}}
+        share = len(lvl1) * dur_ms / ms_per_step
+        # ncu --set full capture of this launch (profiles/r1d_edge_pair_v3_ncu.txt): dram read + write bytes
+        traffic = 8.006e9 if (E, N, H) == (6_000_000, 1_000_000, 128) else None
+    else:
+        def launch():
+            ops.mp(arg["ep"], arg["np_"], topo, arg["e_in"], arg["v_in"], arg["v_in"], act_e="selu", act_t="selu",
+                   want_e=True, precision=eng.precision, e_out=arg["e_out"], t_out=arg["v_out"])
+
+        dur_ms = _time_launch(launch, dev, reps=5)
+        alg_bytes = 4 * H * (2 * E + 2 * N) + 4 * E + (0 if topo.fixed_k else 4 * N)
+        flops = 2 * E * (3 * H * H + 2 * H * H) + 2 * N * (2 * H * H + 2 * H * H)
+        kernel = "mp_kernel (g4c_mp_fwd: level-1 fused edge MLP + aggregation + node MLP, fp32 FFMA)"
+        extra = {}
+        share = len(lvl1) * dur_ms / ms_per_step
+        traffic = None
     achieved = alg_bytes / (dur_ms * 1e-3) / 1e9
-    n_with_e = sum(1 for s in lvl1 if s[1]["e_out"] is not None)
-    return {"kernel": "mp_kernel (level-1 fused edge-MLP + aggregate + node-MLP)", "bound": "hbm",
-            "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-            "peak_source": src, "traffic": None, "launch_ms": dur_ms, "algorithmic_bytes": alg_bytes,
-            "algorithmic_tflop": flops / 1e12, "achieved_tflops": flops / (dur_ms * 1e-3) / 1e12,
-            "level1_launches_per_step": len(lvl1), "share_of_step": len(lvl1) * dur_ms / ms_per_step,
-            "note": f"{n_with_e} of {len(lvl1)} level-1 launches write e'; share uses this launch's duration for all"}
+    out = {"kernel": kernel, "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+           "frac": achieved / peaks["hbm_gbs"], "peak_source": src, "traffic": traffic, "launch_ms": dur_ms,
+           "algorithmic_bytes": alg_bytes, "algorithmic_tflop": flops / 1e12,
+           "achieved_tflops": flops / (dur_ms * 1e-3) / 1e12, "level1_launches_per_step": len(lvl1),
+           "share_of_step": share,
+           "note": f"{n_with_e} of {len(lvl1)} level-1 launches write e'; share uses this launch's duration for all"}
+    out.update(extra)
+    return out
 
 
 if __name__ == "__main__":

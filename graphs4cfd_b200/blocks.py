@@ -24,7 +24,7 @@ from torch import nn
 from . import ops
 from ._lib import require_cuda_f32
 
-_DEFAULT_PRECISION = "fp32"
+_DEFAULT_PRECISION = "auto"      # tensor cores (fp16x3) when hidden = 128, CUDA-core fp32 kernels otherwise
 
 
 def _act_code(activation: Optional[Callable]):
@@ -337,7 +337,7 @@ def _convert(mod: nn.Module, precision: str):
     return new
 
 
-def accelerate(model: nn.Module, precision: str = "fp32") -> nn.Module:
+def accelerate(model: nn.Module, precision: str = "auto") -> nn.Module:
     """Replace every graphs4cfd block of ``model`` by its libg4c counterpart, in place, keeping the
     Parameters and state-dict keys.  ``model.forward``/``solve`` then run unchanged reference code
     between fused blocks."""

@@ -325,9 +325,14 @@ def _seg_struct(t: torch.Tensor, gather, scale) -> L.Seg:
     return s
 
 
-def rowmlp(pack: MlpPack, segs, rows: Optional[int] = None, act=None, out=None, residual=None, precision="fp32"):
+def rowmlp(pack: MlpPack, segs, rows: Optional[int] = None, act=None, out=None, residual=None, precision="auto"):
     """out = act(MLP(cat(segs, dim=-1)) [+ residual]); segs = [(tensor[*, w], gather_idx|None, scale)].
-    precision "fp16x3" runs the tensor-core row kernel (hidden 128); "fp32" the CUDA-core one."""
+    precision "fp16x3" runs the tensor-core row kernel (hidden 128); "fp32" the CUDA-core one; "auto" picks the
+    tensor-core kernel whenever it supports the shape."""
+    if precision == "auto":
+        widths = [int(s[0].shape[1]) for s in segs]
+        ok = pack.tc_row_ok(widths) and not (residual is not None and pack.out_width == 128)
+        precision = "fp16x3" if ok else "fp32"
     if precision == "fp16x3":
         widths = [int(s[0].shape[1]) for s in segs]
         if not pack.tc_row_ok(widths) or (residual is not None and pack.out_width == 128):
@@ -357,13 +362,15 @@ def rowmlp(pack: MlpPack, segs, rows: Optional[int] = None, act=None, out=None, 
 
 
 def mp(edge_pack: MlpPack, node_pack: MlpPack, topo: MpTopo, e_in, src_feat, tgt_feat, aggr="mean",
-       act_e=None, act_t=None, want_e=True, precision="fp32", e_out=None, t_out=None, ws=None):
-    """Message-passing block.  precision "fp32": one fused CUDA-core kernel (g4c_mp_fwd); "fp16x3": the tensor-core
+       act_e=None, act_t=None, want_e=True, precision="auto", e_out=None, t_out=None, ws=None):
+    """Message-passing block.  precision "auto" (default): "fp16x3" when hidden = 128, else "fp32".  "fp32": one fused CUDA-core kernel (g4c_mp_fwd); "fp16x3": the tensor-core
     path = per-node products of the split first edge layer (g4c_rowmlp_tc_fwd x2), fused edge MLP + aggregation
     (g4c_edge_aggr_fwd), node model (g4c_rowmlp_tc_fwd).  ``ws`` = optional preallocated (P_r, P_c, agg).
     Returns (t_out, e_out|None)."""
     L.require_cuda_f32(e_in, src_feat, tgt_feat)
     H = edge_pack.hidden
+    if precision == "auto":
+        precision = "fp16x3" if (edge_pack.tc_edge_ok() and node_pack.tc_row_ok([128, 128])) else "fp32"
     if precision == "fp16x3":
         if not (edge_pack.tc_edge_ok() and node_pack.tc_row_ok([128, 128])):
             raise RuntimeError(f"mp: precision fp16x3 needs hidden=128 (got {H}); use precision='fp32'")

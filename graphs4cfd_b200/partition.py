@@ -366,6 +366,7 @@ class _CudaBackend:
         from . import ops
         eng = self.eng
         ep, npk, topo = eng.pack(name + ".edge_mlp"), eng.pack(name + ".node_mlp"), eng.topos[level]
+        eng.mp_args.append(dict(ep=ep, np_=npk, topo=topo, e_in=e_in, v_in=v_in, e_out=e_out, v_out=v_out))    # for bench.py's roofline
         self.steps.append(lambda: ops.mp(ep, npk, topo, e_in, v_in, v_in, act_e="selu", act_t="selu",
                                          want_e=e_out is not None, precision=eng.precision, e_out=e_out, t_out=v_out))
 
@@ -396,12 +397,14 @@ class _CudaBackend:
 class PartitionedRollout:
     """Rank-local slice of a MuS-GNN rollout.  API mirrors Rollout (solve / step_only / pred / node_in)."""
 
-    def __init__(self, params, graph, rank: int, world: int, precision="fp32", device="cuda", cuda_graph=False):
+    def __init__(self, params, graph, rank: int, world: int, precision="auto", device="cuda", cuda_graph=False):
         from . import ops
         self.device = torch.device(device)
         self.rank, self.world, self.precision = rank, world, precision
         self.params = {k: v.to(self.device) for k, v in params.items()}
         self.H = hidden_width(self.params)
+        if self.precision == "auto":
+            self.precision = "fp16x3" if self.H == 128 else "fp32"
         self.packs = {}
         plans, self.prog = build_rank_plans(graph, params, world)
         self.plan = plan = plans[rank]
@@ -425,6 +428,7 @@ class PartitionedRollout:
         self.parent_local = {l: i32(L[l]["parent_local"]) for l in range(len(L) - 1)}
         self.buffer_bytes = 0
         self.exchanges_per_step = 0
+        self.mp_args = []
         e0_rows = L[0]["eglob"].size + L[0].get("n_edge_recv", 0)
         self.e0 = torch.zeros(max(e0_rows, 1), self.H, device=dev, dtype=torch.float32)
         ops.rowmlp(self.pack("edge_encoder"), [(edge_attr.to(dev), None, 1.0)], act="selu", out=self.e0)

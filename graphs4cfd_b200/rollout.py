@@ -56,13 +56,15 @@ class _Level:
 
 
 class Rollout:
-    def __init__(self, model_or_params, graph, precision: str = "fp32", device="cuda", cuda_graph: bool = True):
+    def __init__(self, model_or_params, graph, precision: str = "auto", device="cuda", cuda_graph: bool = True):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("Rollout needs a CUDA device; graphs4cfd_b200 has no CPU path")
         self.params = {k: v.to(self.device) for k, v in _state_of(model_or_params).items()}
-        self.precision = precision
         self.H = hidden_width(self.params)
+        if precision == "auto":           # tensor cores (fp16x3) for the shipped hidden width, CUDA cores otherwise
+            precision = "fp16x3" if self.H == 128 else "fp32"
+        self.precision = precision
         self.prog = block_program(self.params)
         self.packs = {}
         self._ws = {}
