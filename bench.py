@@ -239,9 +239,17 @@ def run_g4c(a):
                 "e2e": {"value": e2e_val, "unit": "steps/s", "h2d_bytes_per_step": N_local * fw * 4 * world,
                         "d2h_bytes_per_step": N_local * nf * 4 * world, "steps": e2e_steps},
                 "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cb}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Tearing the NCCL communicator down while CUDA graphs that captured its kernels are alive can hang
+        # (seen at N=2: the line above printed, then destroy_process_group never returned).  Every rank has
+        # finished its device work here: synchronise, meet once more, and leave without the teardown.
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        torch.cuda.synchronize(dev)
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def _peaks():
