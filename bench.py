@@ -34,6 +34,9 @@ def parse():
     ap.add_argument("--hidden", type=int, default=128)
     ap.add_argument("--k", type=int, default=6)
     ap.add_argument("--levels", type=int, default=3)
+    ap.add_argument("--model", default="mus", choices=["mus", "remus"],
+                    help="mus: the MuS-GNN workload of BASELINE.json's metric (default); remus: the 3-scale REMuS-GNN of "
+                         "configs[2] (single GPU only; a measurement case, not the driver's bench line)")
     ap.add_argument("--precision", default=os.environ.get("G4C_PRECISION", "auto"),
                     help="auto (fp16x3 tensor-core path when hidden=128, else fp32) | fp16x3 | fp32")
     ap.add_argument("--no-graph", action="store_true")
@@ -43,7 +46,19 @@ def parse():
 
 
 def workload_name(a):
+    if a.model == "remus":
+        return (f"remus3-gnn rollout step, {a.nodes}-node/{a.nodes * a.k}-edge/{a.nodes * a.k * a.k}-angle synthetic kNN mesh, "
+                f"hidden={a.hidden}")
     return f"mus{a.levels}-gnn rollout step, {a.nodes}-node/{a.nodes * a.k}-edge synthetic kNN mesh, hidden={a.hidden}"
+
+
+def build_workload(a, n):
+    """(mesh, parameters) of the benchmarked model on an n-node synthetic mesh (seeded default-init weights)."""
+    from graphs4cfd_b200 import mesh as M
+    from graphs4cfd_b200.archs import init_params, mus_arch, remus_arch
+    if a.model == "remus":
+        return M.build_remus_mesh(n, a.k, seed=0), init_params(remus_arch(a.hidden), seed=0)
+    return M.build_mus_mesh(n, a.k, M.auto_cells(n, a.levels), seed=0), init_params(mus_arch(a.hidden, a.levels), seed=0)
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -92,13 +107,10 @@ def cpu_steps_per_s(a, steps, warmup, sample_nodes):
     """Oracle port (reference op sequence in plain torch, all host threads) on a bounded sample of the
     workload: the same model on a `sample_nodes` mesh; steps/s scaled linearly in N to the full mesh
     (the reference's cost is linear in nodes/edges: BASELINE.md §2)."""
-    from graphs4cfd_b200 import mesh as M
-    from graphs4cfd_b200.archs import init_params, mus_arch
     from oracle import restate as R
     torch.set_num_threads(os.cpu_count() or 1)
     n = min(sample_nodes, a.nodes)
-    g = M.build_mus_mesh(n, a.k, M.auto_cells(n, a.levels), seed=0)
-    params = init_params(mus_arch(a.hidden, a.levels), seed=0)
+    g, params = build_workload(a, n)
     with torch.no_grad():
         for _ in range(warmup):
             R.forward(params, g)
@@ -109,7 +121,7 @@ def cpu_steps_per_s(a, steps, warmup, sample_nodes):
         dt = (time.perf_counter() - t0) / steps
     scale = n / a.nodes
     return {"value": (1.0 / dt) * scale, "unit": "steps/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{steps} steps of the same {a.levels}-scale MuS-GNN (hidden={a.hidden}) on a {n}-node mesh, "
+            "sample": f"{steps} steps of the same {'3-scale REMuS-GNN' if a.model == 'remus' else str(a.levels) + '-scale MuS-GNN'} (hidden={a.hidden}) on a {n}-node mesh, "
                       f"{dt:.3f} s/step measured; steps/s scaled x{scale:.4g} (linear in nodes) to {a.nodes} nodes"}, dt / scale
 
 
@@ -133,8 +145,6 @@ def run_reference(a):
 def run_g4c(a):
     import torch.distributed as dist
     from graphs4cfd_b200 import Rollout, ops
-    from graphs4cfd_b200 import mesh as M
-    from graphs4cfd_b200.archs import init_params, mus_arch
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -144,8 +154,9 @@ def run_g4c(a):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    g = M.build_mus_mesh(a.nodes, a.k, M.auto_cells(a.nodes, a.levels), seed=0)
-    params = init_params(mus_arch(a.hidden, a.levels), seed=0)
+    g, params = build_workload(a, a.nodes)
+    if world > 1 and a.model != "mus":
+        raise SystemExit("bench.py: --model remus runs on one GPU (the node-range partition covers the MuS-GNN models)")
     if world > 1:
         from graphs4cfd_b200.partition import PartitionedRollout
         eng = PartitionedRollout(params, g, rank=rank, world=world, precision=a.precision, device=dev,
@@ -234,7 +245,9 @@ def run_g4c(a):
                 "config": {"workload": workload_name(a), "precision": eng.precision,
                            "parallelism": f"node-range partition x{world}" if world > 1 else "single GPU",
                            "cuda_graph": not a.no_graph, "weights": "seeded default init",
-                           "l2": "inputs larger than L2 (level-1 edge features %.1f GB per buffer)" % (a.nodes * a.k * a.hidden * 4 / 1e9)},
+                           "l2": "inputs larger than L2 (level-1 %s features %.1f GB per buffer)" % (
+                               ("angle", a.nodes * a.k * a.k * a.hidden * 4 / 1e9) if a.model == "remus"
+                               else ("edge", a.nodes * a.k * a.hidden * 4 / 1e9))},
                 "clocks": clocks,
                 "e2e": {"value": e2e_val, "unit": "steps/s", "h2d_bytes_per_step": N_local * fw * 4 * world,
                         "d2h_bytes_per_step": N_local * nf * 4 * world, "steps": e2e_steps},
