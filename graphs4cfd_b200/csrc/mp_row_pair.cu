@@ -70,7 +70,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) row_pair_kern
         }
         fence_barrier_init();
     }
-    if (warp == 12) { tmem_alloc<2>(&s.tmem_base, 512); tmem_relinquish<2>(); }
+    if (warp == W_MMA) { tmem_alloc<2>(&s.tmem_base, 512); tmem_relinquish<2>(); }
     if (tid == 0) {
         // this CTA's half of every layer: layer l is stored [rank][...] in global memory
         mbar_arrive_expect_tx(&s.w_full, a.w_bytes);
@@ -103,7 +103,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) row_pair_kern
                     if (c >= nch) continue;
                     const int64_t R = ((ptb + c * pt_stride) * 2 + rank) * 128 + row;     // this thread's global row
                     const uint32_t d_addr = tmem + lane_base + 256u * c + 64u * half;
-                    mbar_wait(&s.d_full[c], n_dfull[c] & 1);
+                    mbar_wait_sleep(&s.d_full[c], n_dfull[c] & 1);
                     ++n_dfull[c];
                     tc_fence_after();
                     if (l < nl - 1) {
@@ -149,6 +149,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) row_pair_kern
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive_cluster(leader_d_free[c]);
+                        float rstd = 1.f;
                         if (gamma) {
                             float sum = 0.f;
 #pragma unroll
@@ -164,24 +165,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) row_pair_kern
                             }
                             s.part[1][half][row] = sq;
                             epi_sync();
-                            const float rstd = 1.f / sqrtf((s.part[1][0][row] + s.part[1][1][row]) * (1.f / H) + kLnEps);
-#pragma unroll
-                            for (int i = 0; i < 64; i += 4) {
-                                const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + i));
-                                const float4 b = __ldg(reinterpret_cast<const float4*>(beta + i));
-                                y[i] = fmaf(y[i] * rstd, g.x, b.x);
-                                y[i + 1] = fmaf(y[i + 1] * rstd, g.y, b.y);
-                                y[i + 2] = fmaf(y[i + 2] * rstd, g.z, b.z);
-                                y[i + 3] = fmaf(y[i + 3] * rstd, g.w, b.w);
-                            }
+                            rstd = 1.f / sqrtf((s.part[1][0][row] + s.part[1][1][row]) * (1.f / H) + kLnEps);
                         }
                         if (R < d.rows) {
                             float* dst = d.out + (size_t)R * d.out_stride + half * 64;
 #pragma unroll
-                            for (int i = 0; i < 64; i += 8) {
+                            for (int i = 0; i < 64; i += 8) {          // normalise, activate and store 8 columns at a time
                                 float o[8];
 #pragma unroll
-                                for (int u = 0; u < 8; ++u) o[u] = apply_act_fast(y[i + u], d.act_out);
+                                for (int u = 0; u < 8; ++u) o[u] = y[i + u];
+                                if (gamma) {
+#pragma unroll
+                                    for (int u = 0; u < 8; u += 4) {
+                                        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + i + u));
+                                        const float4 b = __ldg(reinterpret_cast<const float4*>(beta + i + u));
+                                        o[u] = fmaf(o[u] * rstd, g.x, b.x);
+                                        o[u + 1] = fmaf(o[u + 1] * rstd, g.y, b.y);
+                                        o[u + 2] = fmaf(o[u + 2] * rstd, g.z, b.z);
+                                        o[u + 3] = fmaf(o[u + 3] * rstd, g.w, b.w);
+                                    }
+                                }
+#pragma unroll
+                                for (int u = 0; u < 8; ++u) o[u] = apply_act_fast(o[u], d.act_out);
                                 stg256(dst + i, o);
                             }
                         }
@@ -189,37 +194,39 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) row_pair_kern
                 }
             }
         }
-    } else if (warp < 12) {
-        // ====================================================================== loader warps
+    } else if (warp < W_LOAD0 + N_LOAD_WARPS) {
+        // ====================================================================== loader warps: two per row quarter, taking
+        // alternate K-block stages (g even / odd), so twice as many global loads are in flight
         setmaxnreg_dec<kRegsLoad>();
-        const int lw = warp - 8;
+        const int lw = (warp - W_LOAD0) & 3, hf = (warp - W_LOAD0) >> 2;
         const uint32_t leader_full0 = mapa(smem_u32(&s.full[0]), 0);      // full[] is contiguous: + 8 bytes per stage
         uint32_t g = 0;                       // K-block stages produced so far
         mbar_wait(&s.w_full, 0);              // full[] is only signalled once this CTA's weights have landed
         for (int64_t pt = pt0; pt < a.n_pt; pt += pt_stride) {
             const int64_t R_lane = (pt * 2 + rank) * 128 + lw * 32 + lane;     // the row this lane describes
             for (int b = 0; b < NKB; ++b, ++g) {
+                if ((int)(g & 1u) != hf) continue;
                 const KBlock& kb = a.kb[b];
                 const int st = g % NS;
                 uint8_t* img_hi = ring + (size_t)st * STAGE;
                 uint8_t* img_lo = img_hi + IMG;
                 int64_t src_row = -1;
                 if (R_lane < d.rows) src_row = kb.gather ? (int64_t)kb.gather[R_lane] : R_lane;
-                mbar_wait(&s.empty[st], ((g / NS) + 1) & 1);
+                mbar_wait_sleep(&s.empty[st], ((g / NS) + 1) & 1);
                 if (kb.width == 64) {
                     // two rows per warp instruction: lanes 0-15 one row, lanes 16-31 the next
                     const int sub = lane >> 4, l16 = lane & 15;
 #pragma unroll 1
-                    for (int i0 = 0; i0 < 32; i0 += 8) {
-                        float4 x[4];
+                    for (int i0 = 0; i0 < 32; i0 += 16) {
+                        float4 x[8];                    // 8 x 512 B in flight per warp
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
+                        for (int u = 0; u < 8; ++u) {
                             const int64_t sr = __shfl_sync(0xffffffffu, src_row, i0 + 2 * u + sub);
                             x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (sr >= 0) x[u] = __ldg(reinterpret_cast<const float4*>(kb.ptr + (size_t)sr * kb.stride + kb.col0 + l16 * 4));
+                            if (sr >= 0) x[u] = ldg_stream(kb.ptr + (size_t)sr * kb.stride + kb.col0 + l16 * 4);
                         }
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
+                        for (int u = 0; u < 8; ++u) {
                             const int r = lw * 32 + i0 + 2 * u + sub;
                             uint2 h, lo;
                             split2(x[u].x * kb.scale, x[u].y * kb.scale, h.x, lo.x);
@@ -254,7 +261,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) row_pair_kern
         }
     } else {
         setmaxnreg_dec<kRegsMisc>();
-        if (warp == 12 && rank == 0) {
+        if (warp == W_MMA && rank == 0) {
             // ================================================================== MMA / copy issuer (leader CTA)
             const uint32_t idesc = idesc_f16(256, 128), idesc_narrow = idesc_f16(256, 32);
             const uint64_t w_desc = make_desc_sw128(smem_u32(smem));
@@ -269,14 +276,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) row_pair_kern
                         if (c >= nch) continue;
                         const uint32_t d_col = tmem + 256u * c, ah = d_col + 128u, al = d_col + 192u;
                         if (l == 0) {
-                            if (lane == 0) mbar_wait<true>(&s.d_free[c], (n_chain[c] + 1) & 1);
+                            if (lane == 0) mbar_wait_sleep(&s.d_free[c], (n_chain[c] + 1) & 1);
                             ++n_chain[c];
                             for (int b = 0; b < NKB; ++b, ++g) {
                                 if (lane == 0) {
                                     const int st = g % NS;
                                     const int nks = a.kb[b].width == 64 ? 4 : 1;
                                     const uint32_t hb = 32u * (b & 1);
-                                    mbar_wait<true>(&s.full[st], (g / NS) & 1);
+                                    mbar_wait_sleep(&s.full[st], (g / NS) & 1);
                                     tc_fence_after();
                                     const uint64_t sd = ring_desc + (uint64_t)((st * STAGE) >> 4);
 #pragma unroll 1
@@ -298,7 +305,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) row_pair_kern
                             if (lane == 0) umma_commit<2>(&s.d_full[c], 3);
                         } else {
                             if (lane == 0) {
-                                mbar_wait<true>(&s.a_ready[c], n_ar[c] & 1);
+                                mbar_wait_sleep(&s.a_ready[c], n_ar[c] & 1);
                                 tc_fence_after();
                                 // K = 128 from the A operand the epilogue wrote; 64-row images, or 16-row images (N = 32)
                                 const uint32_t kb_bytes = narrow_layer ? 4096u : 2u * HIMG, lo_off = narrow_layer ? 2048u : (uint32_t)HIMG;
@@ -325,7 +332,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) row_pair_kern
 
     tc_fence_before();
     cluster_sync_all();
-    if (warp == 12) tmem_dealloc<2>(tmem, 512);
+    if (warp == W_MMA) tmem_dealloc<2>(tmem, 512);
 }
 
 }  // namespace rp
