@@ -35,6 +35,7 @@
 // in the log2 domain, t = acc * (c * log2 e) + b * log2 e, so that x' = t > 0 ? t * ln 2 : alpha * 2^t - alpha
 // costs FFMA + MUFU.EX2 + FFMA + FSETP + predicated FMUL per element.
 #include <algorithm>
+#include <cstddef>
 #include "tc2_core.cuh"
 #include "mp_pair.h"
 
@@ -50,7 +51,7 @@ constexpr int N_EPI_WARPS = 16;
 constexpr int N_LOAD_WARPS = 8;
 constexpr int W_LOAD0 = 16, W_MMA = 24;
 // registers per thread after setmaxnreg: the CTA's pool is what it was launched with, 896 * 72 = 64512
-// = 512*88 (epilogue) + 256*64 (loaders) + 128*24 (MMA issuer + idle warps)
+// = 512*88 (epilogue) + 256*64 (loaders) + 128*24 (MMA issuer + idle warps); 96/48/24 measured 4 % slower
 #ifndef G4C_EP_REGS_EPI
 #define G4C_EP_REGS_EPI 88
 #define G4C_EP_REGS_LOAD 64
@@ -152,7 +153,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_pair_ker
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     Smem& s = *reinterpret_cast<Smem*>(smem_raw);
     if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    int lane = tid & 31;
     const uint32_t rank = cluster_ctarank();
     const int nl = a.n_layers;
     const int n_units = (int)((a.n_targets + 127) / 128);
@@ -188,14 +190,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_pair_ker
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem = s.tmem_base;
+    // 32-bit shared-space addresses of everything the inner loops touch (see lds_f4 in tc2_core.cuh)
+    const uint32_t sb = smem_u32(smem_raw);
+    const uint32_t a_cst = sb + (uint32_t)offsetof(Smem, cst), a_part = sb + (uint32_t)offsetof(Smem, part);
+    const uint32_t a_in_ready = sb + (uint32_t)offsetof(Smem, in_ready), a_a_ready = sb + (uint32_t)offsetof(Smem, a_ready);
+    const uint32_t a_d_free = sb + (uint32_t)offsetof(Smem, d_free), a_d_full = sb + (uint32_t)offsetof(Smem, d_full);
 
     if (warp < N_EPI_WARPS) {
         // ====================================================================== epilogue warps
         setmaxnreg_inc<kRegsEpi>();
-        const int lq = warp & 3, cq = warp >> 2;
+        // the thread index goes through an (identity) shuffle here: ptxas otherwise rematerialises it with an S2R (a
+        // ~30-cycle round trip) wherever a thread-index-derived address is needed in the inner loops
+        const int etid = __shfl_sync(0xffffffffu, tid, tid & 31);
+        lane = etid & 31;
+        const int lq = (etid >> 5) & 3, cq = etid >> 7;
         const int row = lq * 32 + lane;
         const uint32_t lane_base = (uint32_t)(lq * 32) << 16;
-        const uint32_t leader_a_ready[2] = {mapa(smem_u32(&s.a_ready[0]), 0), mapa(smem_u32(&s.a_ready[1]), 0)};
+        const uint32_t leader_a_ready0 = mapa(a_a_ready, 0);          // chain c: + 8 c
+        const uint32_t my_cst = a_cst + 128u * cq, my_part = a_part + 4u * row;
         uint32_t n_dfull[2] = {0, 0};
         const bool has_ln = a.gamma != nullptr;
         int pbuf = 0;
@@ -219,7 +231,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_pair_ker
                         if (c >= nch) continue;
                         const uint32_t d_addr = tmem + lane_base + 256u * c + 32u * cq;
                         // one warp watches the mbarrier; the other fifteen block on a hardware barrier (no issue slots)
-                        if (warp == 0) mbar_wait_sleep(&s.d_full[c], n_dfull[c] & 1);
+                        if (warp == 0) mbar_wait_sleep_a(a_d_full + 8u * c, n_dfull[c] & 1);
                         ++n_dfull[c];
                         epi_sync_all();
                         tc_fence_after();
@@ -232,10 +244,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_pair_ker
                                 float v[16];
                                 tmem_ld16f(d_addr + 16u * h16, v);
                                 uint32_t hi[8], lo[8];
-                                const float4* bs = reinterpret_cast<const float4*>(s.cst[l] + 32 * cq + 16 * h16);
+                                const uint32_t bs = my_cst + 512u * l + 64u * h16;
 #pragma unroll
                                 for (int i = 0; i < 16; i += 4) {
-                                    const float4 b = bs[i >> 2];
+                                    const float4 b = lds_f4(bs + 4u * i);
                                     const float x0 = selu_over_lambda_l2(fmaf(v[i], c2, b.x));
                                     const float x1 = selu_over_lambda_l2(fmaf(v[i + 1], c2, b.y));
                                     const float x2 = selu_over_lambda_l2(fmaf(v[i + 2], c2, b.z));
@@ -249,24 +261,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_pair_ker
                             tmem_wait_st();
                             tc_fence_before();
                             __syncwarp();
-                            if (lane == 0) mbar_arrive_remote(leader_a_ready[c]);
+                            if (lane == 0) mbar_arrive_remote(leader_a_ready0 + 8u * c);
                             PROF_LAP(2);                     // hidden epilogue
                         } else {
                             // ---- last layer: LayerNorm, aggregation, store.  The accumulator is read once and released
                             // at once (the loaders may refill the chain while the rest of this epilogue runs); the row
                             // statistics (mean / M2 of each 16-column piece, combined with Chan's formula) cross the column
                             // quarters through shared memory and one 128-thread barrier.
-                            const float* bs = s.cst[l] + 32 * cq;
+                            const uint32_t bs = my_cst + 512u * l;
                             float y[32];
                             tmem_ld16_nowait(d_addr, y);
                             tmem_ld16_nowait(d_addr + 16u, y + 16);
                             tmem_wait_ld();
                             tc_fence_before();
                             __syncwarp();
-                            if (lane == 0) mbar_arrive(&s.d_free[c]);
+                            if (lane == 0) mbar_arrive_a(a_d_free + 8u * c);
 #pragma unroll
                             for (int i = 0; i < 32; i += 4) {
-                                const float4 b4 = *reinterpret_cast<const float4*>(bs + i);
+                                const float4 b4 = lds_f4(bs + 4u * i);
                                 y[i] = fmaf(y[i], cl, b4.x);
                                 y[i + 1] = fmaf(y[i + 1], cl, b4.y);
                                 y[i + 2] = fmaf(y[i + 2], cl, b4.z);
@@ -291,17 +303,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_pair_ker
                                     M2h[h16] = sq;
                                 }
                                 const float dm = mh[0] - mh[1];
-                                float* pt = &s.part[pbuf][0][cq][row];
-                                pt[0] = 0.5f * (mh[0] + mh[1]);                       // mean of this thread's 32 columns
-                                pt[4 * H] = (M2h[0] + M2h[1]) + 8.f * dm * dm;         // their M2
+                                const uint32_t pa = my_part + 4096u * pbuf;           // part[pbuf][0][0][row]
+                                sts_f1(pa + 512u * cq, 0.5f * (mh[0] + mh[1]));                       // mean of this thread's 32 columns
+                                sts_f1(pa + 2048u + 512u * cq, (M2h[0] + M2h[1]) + 8.f * dm * dm);     // their M2
                                 PROF_LAP(3);                 // last layer: read + statistics
                                 quarter_sync(lq);
                                 PROF_LAP(4);                 // last layer: barrier
-                                const float* pr = &s.part[pbuf][0][0][row];
-                                const float m0 = pr[0], m1 = pr[H], m2 = pr[2 * H], m3 = pr[3 * H];
+                                const float m0 = lds_f1(pa), m1 = lds_f1(pa + 512u), m2 = lds_f1(pa + 1024u), m3 = lds_f1(pa + 1536u);
                                 mean = 0.25f * ((m0 + m1) + (m2 + m3));
                                 const float d0 = m0 - mean, d1 = m1 - mean, d2 = m2 - mean, d3 = m3 - mean;
-                                const float M2 = ((pr[4 * H] + pr[5 * H]) + (pr[6 * H] + pr[7 * H])) +
+                                const float M2 = ((lds_f1(pa + 2048u) + lds_f1(pa + 2560u)) + (lds_f1(pa + 3072u) + lds_f1(pa + 3584u))) +
                                                  32.f * ((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3));
                                 rstd = 1.f / sqrtf(M2 * (1.f / H) + kLnEps);
                                 pbuf ^= 1;
@@ -314,6 +325,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_pair_ker
                                 const int erow = a.edge_perm ? a.edge_perm[slot] : slot;
                                 dst = a.e_out + (size_t)erow * H + cq * 32;
                             }
+                            const bool selu_out = a.act_e_out == G4C_ACT_SELU;
 #pragma unroll
                             for (int i8 = 0; i8 < 32; i8 += 8) {              // 8 columns at a time
                                 float o[8];
@@ -322,8 +334,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_pair_ker
                                 if (has_ln) {
 #pragma unroll
                                     for (int u = 0; u < 8; u += 4) {
-                                        const float4 g = *reinterpret_cast<const float4*>(s.cst[3] + 32 * cq + i8 + u);
-                                        const float4 be = *reinterpret_cast<const float4*>(s.cst[4] + 32 * cq + i8 + u);
+                                        const float4 g = lds_f4(my_cst + 1536u + 4u * (i8 + u));
+                                        const float4 be = lds_f4(my_cst + 2048u + 4u * (i8 + u));
                                         o[u] = fmaf((o[u] - mean) * rstd, g.x, be.x);
                                         o[u + 1] = fmaf((o[u + 1] - mean) * rstd, g.y, be.y);
                                         o[u + 2] = fmaf((o[u + 2] - mean) * rstd, g.z, be.z);
@@ -334,8 +346,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_pair_ker
 #pragma unroll
                                     for (int u = 0; u < 8; ++u) agg[i8 + u] += o[u];
                                     if (dst) {
+                                        if (selu_out) {
 #pragma unroll
-                                        for (int u = 0; u < 8; ++u) o[u] = apply_act_fast(o[u], a.act_e_out);
+                                            for (int u = 0; u < 8; ++u) o[u] = selu_fast(o[u]);
+                                        }
                                         stg256(dst + i8, o);
                                     }
                                 }
@@ -367,7 +381,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_pair_ker
         const float ps = a.p_scale;
         const uint32_t lane_base = (uint32_t)(lw * 32) << 16;
         const uint32_t ring0 = smem_u32(s.ring[warp - W_LOAD0][0]);
-        const uint32_t leader_in_ready[2] = {mapa(smem_u32(&s.in_ready[0]), 0), mapa(smem_u32(&s.in_ready[1]), 0)};
+        const uint32_t leader_in_ready0 = mapa(a_in_ready, 0);        // chain c: + 8 c
         const int row_in_pair = (int)rank * 128 + lw * 32 + lane;
         const int sub = lane >> 2, piece = lane & 3;      // cp.async: 8 rows per instruction, 4 x 16 B per row piece
         mbar_wait(&s.w_full, 0);           // in_ready is only signalled once this CTA's weights have landed
@@ -490,19 +504,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_pair_ker
                     // previous iteration): it stays in flight for the whole processing of stage q
                     issue_stage(ring0 + ((q + NSTG - 1) % NSTG) * STG);
                     if (cw == 0) {
-                        mbar_wait_sleep(&s.d_free[cc], ((cc ? n_slot1 : n_slot0) + 1) & 1);      // last-layer epilogue of the previous slot on this chain
+                        mbar_wait_sleep_a(a_d_free + 8u * cc, ((cc ? n_slot1 : n_slot0) + 1) & 1);      // last-layer epilogue of the previous slot on this chain
                         tc_fence_after();
                         PROF_LAP(1);                             // waiting for the accumulator to be released
                     }
-                    const uint8_t* st = s.ring[warp - W_LOAD0][q % NSTG] + lane * PITCH;
+                    const uint32_t st = ring0 + (q % NSTG) * STG + lane * PITCH;
 #pragma unroll
                     for (int h8 = 0; h8 < 2; ++h8) {             // 8 columns at a time
                         float4 xe[2], xr[2], xc[2];
 #pragma unroll
                         for (int v4 = 0; v4 < 2; ++v4) {
-                            xe[v4] = *reinterpret_cast<const float4*>(st + h8 * 32 + v4 * 16);
-                            xr[v4] = *reinterpret_cast<const float4*>(st + ARR + h8 * 32 + v4 * 16);
-                            xc[v4] = *reinterpret_cast<const float4*>(st + 2 * ARR + h8 * 32 + v4 * 16);
+                            xe[v4] = lds_f4(st + h8 * 32 + v4 * 16);
+                            xr[v4] = lds_f4(st + ARR + h8 * 32 + v4 * 16);
+                            xc[v4] = lds_f4(st + 2 * ARR + h8 * 32 + v4 * 16);
                         }
                         uint32_t eh[4], el[4], pp[8];
 #pragma unroll
@@ -524,7 +538,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_pair_ker
                     }
                     __syncwarp();                                // stage buffer may be refilled
                     if (cw == NCS_W - 1) {
-                        if (lane == 0) mbar_arrive_remote(leader_in_ready[cc]);
+                        if (lane == 0) mbar_arrive_remote(leader_in_ready0 + 8u * cc);
                         if (cc) ++n_slot1; else ++n_slot0;
                     }
                     PROF_LAP(2);                                 // read back, split / add, TMEM writes, next prefetch
@@ -555,14 +569,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_pair_ker
                             const uint32_t d_col = tmem + 256u * c, ah = d_col + 128u, al = d_col + 192u;
                             if (l == 0) {
                                 if (lane == 0) {
-                                    mbar_wait_sleep(&s.in_ready[c], n_chain[c] & 1);
+                                    mbar_wait_sleep_a(a_in_ready + 8u * c, n_chain[c] & 1);
                                     tc_fence_after();
                                     PROF_LAP(0);             // waiting for the loaders
                                 }
                                 ++n_chain[c];
                             } else {
                                 if (lane == 0) {
-                                    mbar_wait_sleep(&s.a_ready[c], n_ar[c] & 1);
+                                    mbar_wait_sleep_a(a_a_ready + 8u * c, n_ar[c] & 1);
                                     tc_fence_after();
                                     PROF_LAP(1);             // waiting for the epilogue
                                 }
@@ -578,7 +592,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_pair_ker
                                     umma_ts<2>(d_col, al + 8 * ks, wh, idesc, 1u);
                                     umma_ts<2>(d_col, ah + 8 * ks, wl, idesc, 1u);
                                 }
-                                umma_commit<2>(&s.d_full[c], 3);
+                                umma_commit_a<2>(a_d_full + 8u * c, 3);
                                 PROF_LAP(2);                 // issuing
                             }
                             __syncwarp();
@@ -611,6 +625,11 @@ int edge_pair_profile(unsigned long long* out64) {
 }
 
 int edge_pair_launch(const EdgeArgs& a, cudaStream_t st) {
+    if (a.act_e_out != G4C_ACT_NONE && a.act_e_out != G4C_ACT_SELU) {
+        // the models only ever apply F.selu to a block's edge / angle output (nn/mus_gnn.py:321, nn/remus_gnn.py:143)
+        set_error("g4c_edge_aggr_fwd: act_e_out must be none or selu");
+        return G4C_EUNSUPPORTED;
+    }
     static bool configured = false;
     const int smem = (int)sizeof(ep::Smem);
     if (!configured) {

@@ -97,6 +97,44 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) 
     } while (!ok);
 }
 
+// ------------------------------------------------------------------ explicit shared-space accesses by 32-bit address
+// In a cluster kernel a dereference of a generic pointer into shared memory costs an S2R of the CTA's window id
+// plus address arithmetic at every access; hot loops use these instead (address = smem_u32(base) + offset, once).
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float lds_f1(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_f1(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ void mbar_arrive_a(uint32_t addr) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_sleep_a(uint32_t addr, uint32_t parity) {
+    uint32_t spins = 0, ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(ok) : "r"(addr), "r"(parity), "r"(20000u) : "memory");
+        if (!ok && ++spins > kWatchdogSpins) __trap();
+    } while (!ok);
+}
+template <int CG>
+__device__ __forceinline__ void umma_commit_a(uint32_t bar_addr, uint16_t mask = 3) {
+    if (CG == 1)
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr) : "memory");
+    else
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar_addr),
+                     "h"(mask)
+                     : "memory");
+}
+
 // ------------------------------------------------------------------ TMEM management
 template <int CG>
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_holder, uint32_t ncols) {
