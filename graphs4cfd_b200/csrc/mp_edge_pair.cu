@@ -403,7 +403,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_pair_ker
             }
         };
         auto spread_slot = [&](int erow, int srow) {
-#pragma unroll
             vmask = 0;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
