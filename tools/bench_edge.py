@@ -16,6 +16,7 @@ ap.add_argument("--reps", type=int, default=10)
 ap.add_argument("--spread", type=int, default=2000, help="sources are drawn within +-spread of the target id")
 ap.add_argument("--layers", type=int, default=3)
 ap.add_argument("--no-e", action="store_true")
+ap.add_argument("--act", default="selu")
 a = ap.parse_args()
 
 dev = torch.device("cuda")
@@ -37,7 +38,7 @@ agg = torch.empty(n, 128, device=dev)
 
 
 def launch():
-    ops.edge_aggr(pack, topo, e, P_r, P_c, act_e="selu", want_e=not a.no_e, e_out=e_out, agg_out=agg)
+    ops.edge_aggr(pack, topo, e, P_r, P_c, act_e=(None if a.act == "none" else a.act), want_e=not a.no_e, e_out=e_out, agg_out=agg)
 
 
 for _ in range(3):
