@@ -329,11 +329,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_pair_ker
                             }
                             const bool selu_out = a.act_e_out == G4C_ACT_SELU;
 #pragma unroll
-                            for (int i8 = 0; i8 < 32; i8 += 8) {              // 8 columns at a time
-                                float o[8];
-#pragma unroll
-                                for (int u = 0; u < 8; ++u) o[u] = y[i8 + u];
-                                if (has_ln) {
+                            for (int i8 = 0; i8 < 32; i8 += 8) {              // 8 columns at a time, in place: every chunk's store
+                                float* o = y + i8;                            // reads its own registers (no write-after-read stall
+                                if (has_ln) {                                 // behind the previous chunk's pending store)
 #pragma unroll
                                     for (int u = 0; u < 8; u += 4) {
                                         const float4 g = lds_f4(my_cst + 1536u + 4u * (i8 + u));
