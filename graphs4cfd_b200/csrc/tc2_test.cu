@@ -143,7 +143,7 @@ ts_test_kernel(const float* A, const uint8_t* Wpack, float inv_scale, const floa
 struct TestSmem3 {
     uint8_t w[2][2 * HIMG];              // per K-block: hi image | lo image, 64 rows each (this CTA's half of W's rows)
     uint8_t img_a[4][IMG];
-    uint64_t w_full, a_ready, d_full;
+    uint64_t w_full, a_ready, d_full, bench_done;
     uint32_t tmem_base;
 };
 
@@ -159,9 +159,10 @@ pair_test_kernel(const float* A, const uint8_t* Wpair, float inv_scale, float* D
         mbar_init(&s.w_full, 1);
         mbar_init(&s.a_ready, 16);       // 8 compute warps of each CTA
         mbar_init(&s.d_full, 1);
+        mbar_init(&s.bench_done, 1);
         fence_barrier_init();
     }
-    if (warp == 8) { tmem_alloc<2>(&s.tmem_base, 256); tmem_relinquish<2>(); }
+    if (warp == 8) { tmem_alloc<2>(&s.tmem_base, 512); tmem_relinquish<2>(); }
     tc_fence_before();
     cluster_sync_all();
     tc_fence_after();
@@ -234,7 +235,59 @@ pair_test_kernel(const float* A, const uint8_t* Wpair, float inv_scale, float* D
     }
     tc_fence_before();
     cluster_sync_all();
-    if (warp == 8) tmem_dealloc<2>(tmem, 256);
+    // ---- flags bit 2: MMA issue-rate microbenchmark.  After the functional test, the issuer thread repeats the
+    // 24-MMA layer (flags >> 8) times and reports clock cycles per MMA in D[0] (bit 3: the MMAs alternate between two
+    // accumulators instead of chaining on one: separates the dependent-accumulate latency from the pipe rate)
+    // bits 4 / 5 / 6: meanwhile the eight compute warps of both CTAs hammer TMEM with tcgen05.ld / tcgen05.st (columns
+    // 384.., not used by the MMAs) or shared memory with 128-bit loads: what the epilogue and loader warps of the real
+    // kernels do next to the tensor pipe
+    if ((flags & 4) && warp < 8 && (flags & (16 | 32 | 64))) {
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        const int iters = (flags >> 8) * 24 * 64 / 40;         // roughly as long as the MMA loop
+        float acc = 0.f;
+        uint32_t z[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) z[i] = 0;
+        for (int it = 0; it < iters; ++it) {
+            if (flags & 16) {
+                float v[32];
+                tmem_ld32(tmem + lane_base + 384u + (uint32_t)((warp >> 2) * 32), v);
+                acc += v[it & 31];
+            }
+            if (flags & 32) {
+                tmem_st32(tmem + lane_base + 384u + (uint32_t)((warp >> 2) * 32), z);
+                tmem_wait_st();
+            }
+            if (flags & 64) {
+                const float4 q = *reinterpret_cast<const float4*>(s.img_a[it & 3] + ((lane * 144 + it * 16) & (IMG - 16)));
+                acc += q.x + q.w;
+            }
+        }
+        if (acc == 123.456f) D[1] = acc;
+    }
+    if ((flags & 4) && warp == 8 && lane == 0 && rank == 0) {
+        const int reps = flags >> 8;
+        const bool two_acc = (flags & 8) != 0;
+        const uint32_t idesc = idesc_f16(256, 128);
+        const long long t0 = clock64();
+        for (int r = 0; r < reps; ++r)
+            for (int kb = 0; kb < 2; ++kb)
+                for (int j = 0; j < 4; ++j) {
+                    const int ks = kb * 4 + j;
+                    const uint64_t wh = make_desc_sw128(smem_u32(s.w[kb]) + 32 * j);
+                    const uint64_t wl = make_desc_sw128(smem_u32(s.w[kb]) + HIMG + 32 * j);
+                    umma_ts<2>(tmem + D_COL, tmem + AH_COL + 8 * ks, wh, idesc, 1u);
+                    umma_ts<2>(tmem + (two_acc ? 256u : D_COL), tmem + AL_COL + 8 * ks, wh, idesc, 1u);
+                    umma_ts<2>(tmem + D_COL, tmem + AH_COL + 8 * ks, wl, idesc, 1u);
+                }
+        umma_commit<2>(&s.bench_done, 1);
+        mbar_wait(&s.bench_done, 0);
+        const long long t1 = clock64();
+        D[0] = (float)(t1 - t0) / (float)(24 * reps);
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 8) tmem_dealloc<2>(tmem, 512);
 }
 
 }  // namespace tc2
