@@ -312,12 +312,15 @@ def roofline_mp(eng, a, dev, ms_per_step):
                    want_e=True, precision=eng.precision, e_out=arg["e_out"], t_out=arg["v_out"], ws=(P_r, P_c, agg))
 
         dur_ms = _time_launch(launch, dev)
+        n0 = ops.L.launch_count()
+        launch_mp()
+        mp_launches = ops.L.launch_count() - n0
         mp_ms = _time_launch(launch_mp, dev)
         # each tensor touched once: read e, write e', read P_r, P_c, write agg (fp32 rows of H), read src ids
         alg_bytes = 4 * H * (2 * E + 3 * N) + 4 * E + (0 if topo.fixed_k else 4 * N)
         flops = 2 * E * 3 * H * H                     # three K = H layers per edge (the gathered terms cost no MMA)
         kernel = "edge_pair_kernel (g4c_edge_aggr_fwd: level-1 fused edge MLP + LayerNorm + aggregation, e' kept)"
-        extra = {"mp_block_ms": mp_ms, "mp_block_launches": 4,
+        extra = {"mp_block_ms": mp_ms, "mp_block_launches": mp_launches,
                  "tensor": {"issued_fp16_tflops": 3 * flops / (dur_ms * 1e-3) / 1e12, "peak_bf16_tflops": peaks.get("bf16_tflops"),
                             "frac": 3 * flops / (dur_ms * 1e-3) / 1e12 / peaks.get("bf16_tflops", 1590.0),
                             "note": "fp16x3: every product is issued as 3 fp16 MMAs with fp32 accumulation"}}

@@ -58,7 +58,8 @@ class RowTcDesc(C.Structure):
     _fields_ = [("rows", C.c_int64), ("n_segs", C.c_int32), ("n_layers", C.c_int32), ("act_out", C.c_int32),
                 ("out_width", C.c_int32), ("out_stride", C.c_int32), ("res_stride", C.c_int32), ("seg", Seg * MAX_SEGS),
                 ("W", C.c_void_p * 3), ("inv_scale", C.c_float * 3), ("_pad", C.c_int32), ("bias", _f32p * 3),
-                ("gamma", _f32p), ("beta", _f32p), ("out", _f32p), ("residual", _f32p)]
+                ("gamma", _f32p), ("beta", _f32p), ("out", _f32p), ("residual", _f32p), ("out2", _f32p),
+                ("dual", C.c_int32), ("_pad2", C.c_int32)]
 
 
 class SegReduceDesc(C.Structure):

@@ -134,6 +134,11 @@ int g4c_rowmlp_tc_fwd(const G4cRowTcDesc* d, void* stream) {
     for (int l = 0; l < d->n_layers; ++l)
         if (!d->W[l] || !aligned16(d->W[l]) || !d->bias[l]) { set_error("g4c_rowmlp_tc_fwd: bad weights at layer %d", l + 1); return G4C_EINVAL; }
     if ((d->gamma == nullptr) != (d->beta == nullptr)) { set_error("g4c_rowmlp_tc_fwd: gamma/beta must both be set or NULL"); return G4C_EINVAL; }
+    if (d->dual) {
+        if (d->n_layers != 2 || d->n_segs != 1 || d->seg[0].width != 128 || d->out_width != 128 || d->gamma || d->act_out != G4C_ACT_NONE) {
+            set_error("g4c_rowmlp_tc_fwd: dual needs n_layers=2, one 128-wide segment, 128-wide outputs, no LayerNorm / activation"); return G4C_EUNSUPPORTED; }
+        if (!d->out2 || (reinterpret_cast<uintptr_t>(d->out2) & 31)) { set_error("g4c_rowmlp_tc_fwd: dual needs a 32-byte aligned out2"); return G4C_EINVAL; }
+    }
     if (d->rows == 0) return G4C_OK;
     return row_pair_launch(*d, static_cast<cudaStream_t>(stream));
 }

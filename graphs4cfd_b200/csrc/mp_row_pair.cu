@@ -106,7 +106,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) row_pair_kern
                     mbar_wait_sleep(&s.d_full[c], n_dfull[c] & 1);
                     ++n_dfull[c];
                     tc_fence_after();
-                    if (l < nl - 1) {
+                    if (l < nl - 1 && d.dual) {
+                        // ---- first of two bare Linears of the same input: store it, keep the A operand, hand the accumulator back
+                        float y[64];
+                        tmem_ld32f(d_addr, y);
+                        tmem_ld32f(d_addr + 32, y + 32);
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(leader_a_ready[c]);
+                        if (R < d.rows) {
+                            const float inv = d.inv_scale[l];
+                            const float* bias = d.bias[l] + half * 64;
+                            float* dst = d.out + (size_t)R * d.out_stride + half * 64;
+#pragma unroll
+                            for (int i = 0; i < 64; i += 8) {
+                                const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + i));
+                                const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + i + 4));
+                                float o[8] = {fmaf(y[i], inv, b0.x), fmaf(y[i + 1], inv, b0.y), fmaf(y[i + 2], inv, b0.z), fmaf(y[i + 3], inv, b0.w),
+                                              fmaf(y[i + 4], inv, b1.x), fmaf(y[i + 5], inv, b1.y), fmaf(y[i + 6], inv, b1.z), fmaf(y[i + 7], inv, b1.w)};
+                                stg256(dst + i, o);
+                            }
+                        }
+                    } else if (l < nl - 1) {
                         epilogue_hidden(d_addr, tmem + lane_base + 256u * c + 128u + 32u * half,
                                         tmem + lane_base + 256u * c + 192u + 32u * half, d.inv_scale[l], d.bias[l] + half * 64);
                         tc_fence_before();
@@ -168,7 +189,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) row_pair_kern
                             rstd = 1.f / sqrtf((s.part[1][0][row] + s.part[1][1][row]) * (1.f / H) + kLnEps);
                         }
                         if (R < d.rows) {
-                            float* dst = d.out + (size_t)R * d.out_stride + half * 64;
+                            float* dst = (d.dual ? d.out2 : d.out) + (size_t)R * d.out_stride + half * 64;
 #pragma unroll
                             for (int i = 0; i < 64; i += 8) {          // normalise, activate and store 8 columns at a time
                                 float o[8];

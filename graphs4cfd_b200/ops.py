@@ -262,6 +262,26 @@ def rowmlp_tc(pack: RowPairPack, segs, rows: Optional[int] = None, act=None, out
     return out
 
 
+def dual_linear_tc(pack_a: RowPairPack, pack_b: RowPairPack, x: torch.Tensor, out_a=None, out_b=None):
+    """g4c_rowmlp_tc_fwd in dual mode: (x W_a^T + b_a, x W_b^T + b_b) with x [rows, 128] read once."""
+    L.require_cuda_f32(x)
+    assert pack_a.n_layers == 1 and pack_b.n_layers == 1 and pack_a.seg_widths == [128] and pack_b.seg_widths == [128]
+    rows = int(x.shape[0])
+    d = L.RowTcDesc()
+    d.rows, d.n_segs, d.n_layers, d.act_out, d.out_width, d.dual = rows, 1, 2, L.ACTS[None], 128, 1
+    d.seg[0] = _seg_struct(x, None, 1.0)
+    for i, pk in enumerate((pack_a, pack_b)):
+        d.W[i], d.inv_scale[i], d.bias[i] = pk.W_pair[0].data_ptr(), pk.inv_scale[0], pk.bias[0].data_ptr()
+    if out_a is None:
+        out_a = torch.empty(rows, 128, device=x.device, dtype=torch.float32)
+    if out_b is None:
+        out_b = torch.empty(rows, 128, device=x.device, dtype=torch.float32)
+    assert out_a.stride(0) == out_b.stride(0)
+    d.out, d.out2, d.out_stride = out_a.data_ptr(), out_b.data_ptr(), int(out_a.stride(0))
+    L.check(L.lib().g4c_rowmlp_tc_fwd(C.byref(d), L.stream_ptr()))
+    return out_a, out_b
+
+
 def edge_aggr(pack: EdgePairPack, topo: "MpTopo", e_in, P_r, P_c, aggr="mean", act_e=None, want_e=True,
               e_out=None, agg_out=None):
     """g4c_edge_aggr_fwd: returns (agg [n_targets,128], e_out|None)."""
@@ -377,8 +397,15 @@ def mp(edge_pack: MlpPack, node_pack: MlpPack, topo: MpTopo, e_in, src_feat, tgt
         ep, proj_s, proj_t = edge_pack.tc_edge()
         dev = e_in.device
         P_r, P_c, agg = ws if ws is not None else (None, None, None)
-        P_r = rowmlp_tc(proj_s, [(src_feat, None, 1.0)], out=P_r)
-        P_c = rowmlp_tc(proj_t, [(tgt_feat, None, 1.0)], out=P_c)
+        if src_feat is tgt_feat:          # GNBlock / EdgeMP: one pass over the features makes both products
+            if P_r is None:
+                P_r = torch.empty(src_feat.shape[0], 128, device=dev, dtype=torch.float32)
+            if P_c is None:
+                P_c = torch.empty_like(P_r)
+            dual_linear_tc(proj_s, proj_t, src_feat, out_a=P_r, out_b=P_c)
+        else:                             # DownEdgeMP: sources and targets are different levels
+            P_r = rowmlp_tc(proj_s, [(src_feat, None, 1.0)], out=P_r)
+            P_c = rowmlp_tc(proj_t, [(tgt_feat, None, 1.0)], out=P_c)
         if agg is None:
             agg = torch.empty(tgt_feat.shape[0], 128, device=dev, dtype=torch.float32)
         agg, e_out = edge_aggr(ep, topo, e_in, P_r, P_c, aggr=aggr, act_e=act_e, want_e=want_e, e_out=e_out, agg_out=agg)

@@ -256,6 +256,12 @@ typedef struct {
     const float* beta;
     float* out;                       /* [rows, out_width], row stride out_stride floats       */
     const float* residual;            /* narrow output only: [rows, >= out_width] or NULL      */
+    /* dual != 0: two bare Linears of the SAME 128-wide input in one pass (the per-node products P_r = S W1s^T and
+     * P_c = S W1t^T + b1 of the split edge model when source and target features are the same tensor):
+     * n_layers = 2, n_segs = 1 (width 128), out = x W[0]^T + bias[0], out2 = x W[1]^T + bias[1]; no LayerNorm,
+     * no activation; the input is read once. */
+    float* out2;                      /* [rows, 128], row stride out_stride floats             */
+    int32_t dual, _pad2;
 } G4cRowTcDesc;
 
 G4C_API int g4c_version(void);

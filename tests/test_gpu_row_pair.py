@@ -94,3 +94,22 @@ def test_encoder_narrow_input(kin):
 @pytest.mark.parametrize("nout", [1, 3])
 def test_decoder_narrow_output_residual(nout):
     _check(7777, [128], [128, 128, nout], False, None, residual=True)
+
+
+@gpu
+@pytest.mark.parametrize("rows", [1, 300, 70001])
+def test_dual_linear(rows):
+    """Two bare Linears of the same input in one pass (P_r, P_c of the split edge model) against fp64."""
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(rows)
+    la, lb = _lin(128, 128, g, dev), _lin(128, 128, g, dev)
+    x = torch.randn(rows, 128, generator=g).to(dev)
+    pa, pb = ops.RowPairPack([la], [128]), ops.RowPairPack([lb], [128])
+    ya, yb = ops.dual_linear_tc(pa, pb, x)
+    torch.cuda.synchronize()
+    for y, (W, b) in ((ya, la), (yb, lb)):
+        ref = x.double() @ W.double().t() + b.double()
+        err = float((y.double() - ref).norm() / ref.norm())
+        assert err < 2e-5, f"rel-L2 {err:.3e}"
+    # and bit-identical to the single-output kernel
+    assert torch.equal(ya, ops.rowmlp_tc(pa, [(x, None, 1.0)])) and torch.equal(yb, ops.rowmlp_tc(pb, [(x, None, 1.0)]))

@@ -25,3 +25,7 @@ ms = t(lambda: ops.rowmlp_tc(proj, [(v, None, 1.0)], out=P))
 print(f"bare Linear (P_r / P_c): {ms:.3f} ms, {2 * n * 512 / ms / 1e6:.0f} GB/s")
 ms = t(lambda: ops.rowmlp_tc(node, [(agg, None, 1.0), (v, None, 1.0)], act="selu", out=out))
 print(f"node model: {ms:.3f} ms, {3 * n * 512 / ms / 1e6:.0f} GB/s")
+proj2 = ops.RowPairPack([lin(128, 128)], [128])
+P2 = torch.empty(n, 128, device=dev)
+ms = t(lambda: ops.dual_linear_tc(proj, proj2, v, out_a=P, out_b=P2))
+print(f"dual Linear (P_r and P_c in one pass): {ms:.3f} ms, {3 * n * 512 / ms / 1e6:.0f} GB/s")
