@@ -40,10 +40,10 @@ struct Args {
 };
 
 struct Tail {
-    float part[2][2][128];
+    float part[4][128];                 // LayerNorm partials [column quarter][row] (sums, then centred squares)
     uint64_t w_full;
     uint64_t full[4], empty[4];         // full: leader, 8 loader warps of the pair; empty: local, multicast commit
-    uint64_t a_ready[2], d_free[2];     // leader, 16 epilogue warps of the pair
+    uint64_t a_ready[2], d_free[2];     // leader, 32 epilogue warps of the pair
     uint64_t d_full[2];                 // local, multicast commit
     uint32_t tmem_base;
 };
@@ -64,8 +64,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) row_pair_kern
         mbar_init(&s.w_full, 1);
         for (int i = 0; i < 4; ++i) { mbar_init(&s.full[i], 8); mbar_init(&s.empty[i], 1); }
         for (int c = 0; c < 2; ++c) {
-            mbar_init(&s.a_ready[c], 16);
-            mbar_init(&s.d_free[c], 16);
+            mbar_init(&s.a_ready[c], 2 * N_EPI_WARPS);
+            mbar_init(&s.d_free[c], 2 * N_EPI_WARPS);
             mbar_init(&s.d_full[c], 1);
         }
         fence_barrier_init();
@@ -84,16 +84,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) row_pair_kern
     tc_fence_after();
     const uint32_t tmem = s.tmem_base;
 
-    if (warp < 8) {
-        // ====================================================================== epilogue warps
+    if (warp < N_EPI_WARPS) {
+        // ====================================================================== epilogue warps: thread (row, column quarter)
         setmaxnreg_inc<kRegsEpi>();
-        const int row = (warp & 3) * 32 + lane, half = warp >> 2;
-        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        const int lq = warp & 3, cq = warp >> 2;
+        const int row = lq * 32 + lane;
+        const uint32_t lane_base = (uint32_t)(lq * 32) << 16;
         const uint32_t leader_a_ready[2] = {mapa(smem_u32(&s.a_ready[0]), 0), mapa(smem_u32(&s.a_ready[1]), 0)};
         const uint32_t leader_d_free[2] = {mapa(smem_u32(&s.d_free[0]), 0), mapa(smem_u32(&s.d_free[1]), 0)};
         uint32_t n_dfull[2] = {0, 0};
-        const float* gamma = d.gamma ? d.gamma + half * 64 : nullptr;
-        const float* beta = d.beta ? d.beta + half * 64 : nullptr;
+        const float* gamma = d.gamma ? d.gamma + cq * 32 : nullptr;
+        const float* beta = d.beta ? d.beta + cq * 32 : nullptr;
 
         for (int64_t ptb = pt0; ptb < a.n_pt; ptb += 2 * pt_stride) {
             const int nch = (ptb + pt_stride < a.n_pt) ? 2 : 1;
@@ -102,24 +103,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) row_pair_kern
                 for (int c = 0; c < 2; ++c) {
                     if (c >= nch) continue;
                     const int64_t R = ((ptb + c * pt_stride) * 2 + rank) * 128 + row;     // this thread's global row
-                    const uint32_t d_addr = tmem + lane_base + 256u * c + 64u * half;
+                    const uint32_t d_addr = tmem + lane_base + 256u * c + 32u * cq;
                     mbar_wait_sleep(&s.d_full[c], n_dfull[c] & 1);
                     ++n_dfull[c];
                     tc_fence_after();
+                    const float inv = d.inv_scale[l];
+                    const float* bias = d.bias[l] + cq * 32;
                     if (l < nl - 1 && d.dual) {
                         // ---- first of two bare Linears of the same input: store it, keep the A operand, hand the accumulator back
-                        float y[64];
+                        float y[32];
                         tmem_ld32f(d_addr, y);
-                        tmem_ld32f(d_addr + 32, y + 32);
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive_cluster(leader_a_ready[c]);
                         if (R < d.rows) {
-                            const float inv = d.inv_scale[l];
-                            const float* bias = d.bias[l] + half * 64;
-                            float* dst = d.out + (size_t)R * d.out_stride + half * 64;
+                            float* dst = d.out + (size_t)R * d.out_stride + cq * 32;
 #pragma unroll
-                            for (int i = 0; i < 64; i += 8) {
+                            for (int i = 0; i < 32; i += 8) {
                                 const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + i));
                                 const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + i + 4));
                                 float o[8] = {fmaf(y[i], inv, b0.x), fmaf(y[i + 1], inv, b0.y), fmaf(y[i + 2], inv, b0.z), fmaf(y[i + 3], inv, b0.w),
@@ -128,20 +128,35 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) row_pair_kern
                             }
                         }
                     } else if (l < nl - 1) {
-                        epilogue_hidden(d_addr, tmem + lane_base + 256u * c + 128u + 32u * half,
-                                        tmem + lane_base + 256u * c + 192u + 32u * half, d.inv_scale[l], d.bias[l] + half * 64);
+                        // ---- hidden layer: x = selu(acc * inv + bias) as fp16 (hi, lo) A operand columns, 16 columns at a time
+#pragma unroll
+                        for (int h16 = 0; h16 < 2; ++h16) {
+                            float v[16];
+                            tmem_ld16f(d_addr + 16u * h16, v);
+                            uint32_t hi[8], lo[8];
+#pragma unroll
+                            for (int i = 0; i < 16; i += 4) {
+                                const float4 b = __ldg(reinterpret_cast<const float4*>(bias + 16 * h16 + i));
+                                const float x0 = selu_fast(fmaf(v[i], inv, b.x)), x1 = selu_fast(fmaf(v[i + 1], inv, b.y));
+                                const float x2 = selu_fast(fmaf(v[i + 2], inv, b.z)), x3 = selu_fast(fmaf(v[i + 3], inv, b.w));
+                                split2(x0, x1, hi[i / 2], lo[i / 2]);
+                                split2(x2, x3, hi[i / 2 + 1], lo[i / 2 + 1]);
+                            }
+                            tmem_st8(tmem + lane_base + 256u * c + 128u + 16u * cq + 8u * h16, hi);
+                            tmem_st8(tmem + lane_base + 256u * c + 192u + 16u * cq + 8u * h16, lo);
+                        }
+                        tmem_wait_st();
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive_cluster(leader_a_ready[c]);
                     } else if (narrow_out) {
-                        // ---- last layer narrower than 16: columns 0..out_width-1 of the N = 32 accumulator
+                        // ---- last layer narrower than 16: columns 0..out_width-1 of the N = 32 accumulator (column quarter 0)
                         float y[16];
-                        if (half == 0) tmem_ld16f(tmem + lane_base + 256u * c, y);
+                        if (cq == 0) tmem_ld16f(tmem + lane_base + 256u * c, y);
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive_cluster(leader_d_free[c]);
-                        if (half == 0 && R < d.rows) {
-                            const float inv = d.inv_scale[l];
+                        if (cq == 0 && R < d.rows) {
 #pragma unroll
                             for (int i = 0; i < 16; ++i) {
                                 if (i < d.out_width) {
@@ -153,57 +168,57 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) row_pair_kern
                             }
                         }
                     } else {
-                        // ---- last layer 128 wide: LayerNorm, activation, store
-                        float y[64];
-                        const float inv = d.inv_scale[l];
-                        const float* bias = d.bias[l] + half * 64;
+                        // ---- last layer 128 wide: LayerNorm (row statistics combined over the four column quarters with Chan's
+                        // formula through shared memory and one 128-thread barrier per row quarter), activation, store
+                        float y[32];
                         tmem_ld32f(d_addr, y);
-                        tmem_ld32f(d_addr + 32, y + 32);
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(leader_d_free[c]);
 #pragma unroll
-                        for (int i = 0; i < 64; i += 4) {
+                        for (int i = 0; i < 32; i += 4) {
                             const float4 b = __ldg(reinterpret_cast<const float4*>(bias + i));
                             y[i] = fmaf(y[i], inv, b.x);
                             y[i + 1] = fmaf(y[i + 1], inv, b.y);
                             y[i + 2] = fmaf(y[i + 2], inv, b.z);
                             y[i + 3] = fmaf(y[i + 3], inv, b.w);
                         }
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive_cluster(leader_d_free[c]);
-                        float rstd = 1.f;
+                        float mean = 0.f, rstd = 1.f;
                         if (gamma) {
+                            // two-pass statistics through ONE 2 KiB array of per-quarter partials (a third ring stage matters
+                            // more to this kernel than a barrier): sums, barrier, read, barrier, centred squares, barrier, read
                             float sum = 0.f;
 #pragma unroll
-                            for (int i = 0; i < 64; ++i) sum += y[i];
-                            s.part[0][half][row] = sum;
-                            epi_sync();
-                            const float mean = (s.part[0][0][row] + s.part[0][1][row]) * (1.f / H);
+                            for (int i = 0; i < 32; ++i) sum += y[i];
+                            s.part[cq][row] = sum;
+                            asm volatile("bar.sync %0, 128;" ::"r"(1 + lq) : "memory");
+                            mean = ((s.part[0][row] + s.part[1][row]) + (s.part[2][row] + s.part[3][row])) * (1.f / H);
+                            asm volatile("bar.sync %0, 128;" ::"r"(1 + lq) : "memory");
                             float sq = 0.f;
 #pragma unroll
-                            for (int i = 0; i < 64; ++i) {
-                                y[i] -= mean;
-                                sq = fmaf(y[i], y[i], sq);
+                            for (int i = 0; i < 32; ++i) {
+                                const float dlt = y[i] - mean;
+                                sq = fmaf(dlt, dlt, sq);
                             }
-                            s.part[1][half][row] = sq;
-                            epi_sync();
-                            rstd = 1.f / sqrtf((s.part[1][0][row] + s.part[1][1][row]) * (1.f / H) + kLnEps);
+                            s.part[cq][row] = sq;
+                            asm volatile("bar.sync %0, 128;" ::"r"(1 + lq) : "memory");
+                            const float var = ((s.part[0][row] + s.part[1][row]) + (s.part[2][row] + s.part[3][row])) * (1.f / H);
+                            rstd = 1.f / sqrtf(var + kLnEps);
                         }
                         if (R < d.rows) {
-                            float* dst = (d.dual ? d.out2 : d.out) + (size_t)R * d.out_stride + half * 64;
+                            float* dst = (d.dual ? d.out2 : d.out) + (size_t)R * d.out_stride + cq * 32;
 #pragma unroll
-                            for (int i = 0; i < 64; i += 8) {          // normalise, activate and store 8 columns at a time
-                                float o[8];
-#pragma unroll
-                                for (int u = 0; u < 8; ++u) o[u] = y[i + u];
+                            for (int i = 0; i < 32; i += 8) {          // normalise, activate and store 8 columns at a time
+                                float* o = y + i;
                                 if (gamma) {
 #pragma unroll
                                     for (int u = 0; u < 8; u += 4) {
                                         const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + i + u));
                                         const float4 b = __ldg(reinterpret_cast<const float4*>(beta + i + u));
-                                        o[u] = fmaf(o[u] * rstd, g.x, b.x);
-                                        o[u + 1] = fmaf(o[u + 1] * rstd, g.y, b.y);
-                                        o[u + 2] = fmaf(o[u + 2] * rstd, g.z, b.z);
-                                        o[u + 3] = fmaf(o[u + 3] * rstd, g.w, b.w);
+                                        o[u] = fmaf((o[u] - mean) * rstd, g.x, b.x);
+                                        o[u + 1] = fmaf((o[u + 1] - mean) * rstd, g.y, b.y);
+                                        o[u + 2] = fmaf((o[u + 2] - mean) * rstd, g.z, b.z);
+                                        o[u + 3] = fmaf((o[u + 3] - mean) * rstd, g.w, b.w);
                                     }
                                 }
 #pragma unroll

@@ -12,12 +12,12 @@ using namespace tc2;
 constexpr int H = 128;
 constexpr int IMG = 128 * 128;          // bytes of a 128-row image
 constexpr int HIMG = 64 * 128;          // bytes of a 64-row image (one CTA's half of a weight K-block)
-constexpr int NT = 640;                 // warps 0-7 epilogue, 8-15 loaders, 16 MMA issuer, 17-19 idle
-constexpr int W_LOAD0 = 8, N_LOAD_WARPS = 8, W_MMA = 16;
-constexpr int NEPI = 256;
-// registers per thread after setmaxnreg: the CTA's pool is what it was launched with, 640 * 96 = 61440
-// = 256*152 (epilogue) + 256*64 (loaders) + 128*48 (MMA issuer + idle warps)
-constexpr int kRegsEpi = 152, kRegsLoad = 64, kRegsMisc = 48;
+constexpr int NT = 896;                 // warps 0-15 epilogue, 16-23 loaders, 24 MMA issuer, 25-27 idle
+constexpr int N_EPI_WARPS = 16, W_LOAD0 = 16, N_LOAD_WARPS = 8, W_MMA = 24;
+constexpr int NEPI = 512;
+// registers per thread after setmaxnreg: the CTA's pool is what it was launched with, 896 * 72 = 64512
+// = 512*80 (epilogue) + 256*64 (loaders) + 128*56 (MMA issuer + idle warps)
+constexpr int kRegsEpi = 80, kRegsLoad = 64, kRegsMisc = 56;
 constexpr int kMaxSmem = 232448;        // 227 KiB opt-in limit
 
 __device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory"); }
