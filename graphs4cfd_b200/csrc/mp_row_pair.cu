@@ -7,8 +7,9 @@
 // MMAs of one tile overlap the epilogue of the other — with these differences:
 //   * a "slot" is a pair-tile (256 consecutive rows, 128 per CTA); the tiles a pair owns alternate chains;
 //   * layer 1 consumes the concatenated input K-block by K-block (64 columns each, or one K = 16 step for a
-//     narrow segment) through a ring of (hi, lo) image stages, so any number of segments streams through the
-//     same 64 TMEM columns of A (K-block b uses half b & 1);
+//     narrow segment): K-block b is written by the loader warps into half b & 1 of the chain's A operand columns
+//     (rows fetched with cp.async into a private ring of 16-column stages, read back with lane = row, split into
+//     fp16 (hi, lo), tcgen05.st), so any number of segments streams through the same 64 TMEM columns of A;
 //   * the last layer is either 128 wide (optional LayerNorm, activation, 256-bit row stores) or narrower than
 //     16 (an N = 16 MMA; bias, optional residual, scalar stores: the decoder, nn/mus_gnn.py:369-373).
 #include <algorithm>
@@ -21,7 +22,11 @@ using namespace tc2;
 using namespace pairk;
 
 constexpr int MAX_KB = 6;
-constexpr int STAGE = 2 * IMG;          // hi image | lo image of one K-block
+constexpr int SCOLS = 16;               // columns per loader stage
+constexpr int PITCH = 80;               // bytes between staged 64-byte row pieces (conflict-free lane = row 16-byte reads)
+constexpr int STG = 32 * PITCH;         // one stage: 32 row pieces
+constexpr int NSTG = 4;                 // stages per loader warp
+constexpr int RING_BYTES = N_LOAD_WARPS * NSTG * STG;
 
 struct KBlock {
     const float* ptr;
@@ -33,7 +38,7 @@ struct KBlock {
 struct Args {
     G4cRowTcDesc d;
     KBlock kb[MAX_KB];
-    int32_t n_kb, n_stage;
+    int32_t n_kb, _pad;
     uint32_t w_off[3];                  // byte offset of each layer's images in the weight region
     uint32_t w_bytes, ring_off, tail_off;
     int64_t n_pt;                       // pair-tiles
@@ -42,7 +47,8 @@ struct Args {
 struct Tail {
     float part[4][128];                 // LayerNorm partials [column quarter][row] (sums, then centred squares)
     uint64_t w_full;
-    uint64_t full[4], empty[4];         // full: leader, 8 loader warps of the pair; empty: local, multicast commit
+    uint64_t full[4], empty[4];         // per A-operand half (2 * chain + half): full = leader, the 8 loader warps of the pair
+                                        // that wrote it; empty = local, multicast commit of the MMAs that read it
     uint64_t a_ready[2], d_free[2];     // leader, 32 epilogue warps of the pair
     uint64_t d_full[2];                 // local, multicast commit
     uint32_t tmem_base;
@@ -52,11 +58,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) row_pair_kern
     extern __shared__ __align__(1024) uint8_t smem[];
     if ((smem_u32(smem) & 1023u) != 0) __trap();
     Tail& s = *reinterpret_cast<Tail*>(smem + a.tail_off);
-    uint8_t* ring = smem + a.ring_off;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = cluster_ctarank();
     const G4cRowTcDesc& d = a.d;
-    const int nl = d.n_layers, NS = a.n_stage, NKB = a.n_kb;
+    const int nl = d.n_layers, NKB = a.n_kb;
     const bool narrow_out = d.out_width != H;
     const int64_t pt0 = blockIdx.x >> 1, pt_stride = gridDim.x >> 1;
 
@@ -232,49 +237,103 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) row_pair_kern
         }
     } else if (warp < W_LOAD0 + N_LOAD_WARPS) {
         // ====================================================================== loader warps: two per row quarter, taking
-        // alternate K-block stages (g even / odd), so twice as many global loads are in flight
+        // alternate K-blocks of the global (tile, K-block) sequence
         setmaxnreg_dec<kRegsLoad>();
         const int lw = (warp - W_LOAD0) & 3, hf = (warp - W_LOAD0) >> 2;
-        const uint32_t leader_full0 = mapa(smem_u32(&s.full[0]), 0);      // full[] is contiguous: + 8 bytes per stage
-        uint32_t g = 0;                       // K-block stages produced so far
+        const uint32_t lane_base = (uint32_t)(lw * 32) << 16;
+        const uint32_t leader_full0 = mapa(smem_u32(&s.full[0]), 0);      // full[] is contiguous: + 8 bytes per buffer
+        const uint32_t ring0 = smem_u32(smem + a.ring_off) + (uint32_t)(warp - W_LOAD0) * (NSTG * STG);
+        const int sub = lane >> 2, piece = lane & 3;                       // cp.async: 8 rows per instruction, 4 x 16 B per piece
         mbar_wait(&s.w_full, 0);              // full[] is only signalled once this CTA's weights have landed
-        for (int64_t pt = pt0; pt < a.n_pt; pt += pt_stride) {
-            const int64_t R_lane = (pt * 2 + rank) * 128 + lw * 32 + lane;     // the row this lane describes
+
+        // ---- issue cursor over this warp's WIDE K-blocks (narrow ones are loaded directly), NSTG - 1 stages ahead
+        int64_t i_pt = pt0;
+        int i_b = -1, i_cs = 0;
+        uint32_t i_g = 0xffffffffu, off[4], vmask = 0;     // 16-byte-unit offsets of this lane's pieces of tile rows 8 i + sub
+        bool i_live = true;
+        auto seek_kblock = [&]() {            // next wide K-block of this warp at or after the cursor
+            while (true) {
+                ++i_b; ++i_g;
+                if (i_b == NKB) { i_b = 0; i_pt += pt_stride; }
+                if (i_pt >= a.n_pt) { i_live = false; return; }
+                if ((int)(i_g & 1u) == hf && a.kb[i_b].width == 64) break;
+            }
+            const KBlock& kb = a.kb[i_b];
+            vmask = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int64_t R = (i_pt * 2 + rank) * 128 + lw * 32 + 8 * i + sub;
+                const bool ok = R < d.rows;
+                const int64_t sr = ok ? (kb.gather ? (int64_t)__ldg(kb.gather + R) : R) : 0;
+                vmask |= ok ? (1u << i) : 0u;
+                off[i] = (uint32_t)((sr * kb.stride + kb.col0) >> 2) + piece;
+            }
+            i_cs = 0;
+        };
+        auto issue_stage = [&](uint32_t stage_addr) {
+            if (i_live) {
+                const char* base = reinterpret_cast<const char*>(a.kb[i_b].ptr) + i_cs * (SCOLS * 4);
+                const uint32_t dst0 = stage_addr + (uint32_t)sub * PITCH + piece * 16;
+                const float* p0 = reinterpret_cast<const float*>(base + (size_t)off[0] * 16);
+                const float* p1 = reinterpret_cast<const float*>(base + (size_t)off[1] * 16);
+                const float* p2 = reinterpret_cast<const float*>(base + (size_t)off[2] * 16);
+                const float* p3 = reinterpret_cast<const float*>(base + (size_t)off[3] * 16);
+                asm volatile(
+                    "cp.async.cg.shared.global [%0], [%1], 16, %5;\n\t"
+                    "cp.async.cg.shared.global [%0 + 640], [%2], 16, %6;\n\t"
+                    "cp.async.cg.shared.global [%0 + 1280], [%3], 16, %7;\n\t"
+                    "cp.async.cg.shared.global [%0 + 1920], [%4], 16, %8;\n"
+                    ::"r"(dst0), "l"(p0), "l"(p1), "l"(p2), "l"(p3), "r"((vmask & 1u) ? 16u : 0u), "r"((vmask & 2u) ? 16u : 0u),
+                    "r"((vmask & 4u) ? 16u : 0u), "r"((vmask & 8u) ? 16u : 0u)
+                    : "memory");
+                static_assert(8 * PITCH == 640, "offsets in the cp.async block above");
+                if (++i_cs == 4) seek_kblock();
+            }
+            cp_async_commit();              // one (possibly empty) group per stage keeps the wait depth constant
+        };
+        seek_kblock();
+#pragma unroll 1
+        for (int p = 0; p < NSTG - 1; ++p) issue_stage(ring0 + p * STG);
+
+        uint32_t g = 0, q = 0, ubits = 0;     // K-blocks seen, ring stages consumed, use parity of the four A-operand halves
+        int tile_ord = 0;
+        for (int64_t pt = pt0; pt < a.n_pt; pt += pt_stride, ++tile_ord) {
+            const int c = tile_ord & 1;
             for (int b = 0; b < NKB; ++b, ++g) {
+                const int buf = 2 * c + (b & 1);
+                const uint32_t upar = (ubits >> buf) & 1u;
+                ubits ^= 1u << buf;
                 if ((int)(g & 1u) != hf) continue;
                 const KBlock& kb = a.kb[b];
-                const int st = g % NS;
-                uint8_t* img_hi = ring + (size_t)st * STAGE;
-                uint8_t* img_lo = img_hi + IMG;
-                int64_t src_row = -1;
-                if (R_lane < d.rows) src_row = kb.gather ? (int64_t)kb.gather[R_lane] : R_lane;
-                mbar_wait_sleep(&s.empty[st], ((g / NS) + 1) & 1);
+                const uint32_t ah = tmem + lane_base + 256u * c + 128u + 32u * (b & 1), al = ah + 64u;
+                // the MMAs of the previous use of this half (or, for the last K-blocks of a tile, of its last layer) are done
+                mbar_wait_sleep(&s.empty[buf], upar ^ 1u);
+                tc_fence_after();
                 if (kb.width == 64) {
-                    // two rows per warp instruction: lanes 0-15 one row, lanes 16-31 the next
-                    const int sub = lane >> 4, l16 = lane & 15;
 #pragma unroll 1
-                    for (int i0 = 0; i0 < 32; i0 += 16) {
-                        float4 x[8];                    // 8 x 512 B in flight per warp
+                    for (int cs = 0; cs < 4; ++cs, ++q) {
+                        cp_async_wait<NSTG - 2>();
+                        __syncwarp();
+                        const uint32_t st = ring0 + (q % NSTG) * STG + lane * PITCH;
+                        float4 x[4];
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            const int64_t sr = __shfl_sync(0xffffffffu, src_row, i0 + 2 * u + sub);
-                            x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (sr >= 0) x[u] = ldg_stream(kb.ptr + (size_t)sr * kb.stride + kb.col0 + l16 * 4);
-                        }
+                        for (int v4 = 0; v4 < 4; ++v4) x[v4] = lds_f4(st + v4 * 16);
+                        __syncwarp();                                    // every lane has read stage q: refill the buffer of stage q - 1 ... q + 3
+                        issue_stage(ring0 + ((q + NSTG - 1) % NSTG) * STG);
+                        uint32_t h[8], lo[8];
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            const int r = lw * 32 + i0 + 2 * u + sub;
-                            uint2 h, lo;
-                            split2(x[u].x * kb.scale, x[u].y * kb.scale, h.x, lo.x);
-                            split2(x[u].z * kb.scale, x[u].w * kb.scale, h.y, lo.y);
-                            const uint32_t off = img_off(r, l16 >> 1) + (l16 & 1) * 8;
-                            *reinterpret_cast<uint2*>(img_hi + off) = h;
-                            *reinterpret_cast<uint2*>(img_lo + off) = lo;
+                        for (int v4 = 0; v4 < 4; ++v4) {
+                            split2(x[v4].x * kb.scale, x[v4].y * kb.scale, h[2 * v4], lo[2 * v4]);
+                            split2(x[v4].z * kb.scale, x[v4].w * kb.scale, h[2 * v4 + 1], lo[2 * v4 + 1]);
                         }
+                        tmem_st8(ah + 8u * cs, h);
+                        tmem_st8(al + 8u * cs, lo);
                     }
                 } else {
-                    // narrow segment: lane = row, one K = 16 step (32 bytes per image row)
-                    const int r = lw * 32 + lane;
+                    // narrow segment: lane = row, one K = 16 step, scalar loads (rows need not be 16-byte aligned)
+                    const int64_t R = (pt * 2 + rank) * 128 + lw * 32 + lane;
+                    int64_t src_row = -1;
+                    if (R < d.rows) src_row = kb.gather ? (int64_t)kb.gather[R] : R;
                     uint32_t h[8], lo[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
@@ -285,24 +344,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) row_pair_kern
                         }
                         split2(x0, x1, h[i], lo[i]);
                     }
-                    *reinterpret_cast<uint4*>(img_hi + img_off(r, 0)) = make_uint4(h[0], h[1], h[2], h[3]);
-                    *reinterpret_cast<uint4*>(img_hi + img_off(r, 1)) = make_uint4(h[4], h[5], h[6], h[7]);
-                    *reinterpret_cast<uint4*>(img_lo + img_off(r, 0)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                    *reinterpret_cast<uint4*>(img_lo + img_off(r, 1)) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+                    tmem_st8(ah, h);
+                    tmem_st8(al, lo);
                 }
-                fence_proxy_async();
+                tmem_wait_st();
+                tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(leader_full0 + 8u * (uint32_t)st);
+                if (lane == 0) mbar_arrive_cluster(leader_full0 + 8u * (uint32_t)buf);
             }
         }
+        cp_async_wait<0>();
     } else {
         setmaxnreg_dec<kRegsMisc>();
         if (warp == W_MMA && rank == 0) {
-            // ================================================================== MMA / copy issuer (leader CTA)
+            // ================================================================== MMA issuer (leader CTA)
             const uint32_t idesc = idesc_f16(256, 128), idesc_narrow = idesc_f16(256, 32);
             const uint64_t w_desc = make_desc_sw128(smem_u32(smem));
-            const uint64_t ring_desc = make_desc_sw128(smem_u32(ring));
-            uint32_t g = 0, n_chain[2] = {0, 0}, n_ar[2] = {0, 0};
+            uint32_t ubits = 0, n_chain[2] = {0, 0}, n_ar[2] = {0, 0};
             for (int64_t ptb = pt0; ptb < a.n_pt; ptb += 2 * pt_stride) {
                 const int nch = (ptb + pt_stride < a.n_pt) ? 2 : 1;
                 for (int l = 0; l < nl; ++l) {
@@ -314,19 +372,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) row_pair_kern
                         if (l == 0) {
                             if (lane == 0) mbar_wait_sleep(&s.d_free[c], (n_chain[c] + 1) & 1);
                             ++n_chain[c];
-                            for (int b = 0; b < NKB; ++b, ++g) {
+                            for (int b = 0; b < NKB; ++b) {
+                                const int buf = 2 * c + (b & 1);
+                                const uint32_t upar = (ubits >> buf) & 1u;
+                                ubits ^= 1u << buf;
                                 if (lane == 0) {
-                                    const int st = g % NS;
                                     const int nks = a.kb[b].width == 64 ? 4 : 1;
                                     const uint32_t hb = 32u * (b & 1);
-                                    mbar_wait_sleep(&s.full[st], (g / NS) & 1);
+                                    mbar_wait_sleep(&s.full[buf], upar);
                                     tc_fence_after();
-                                    const uint64_t sd = ring_desc + (uint64_t)((st * STAGE) >> 4);
-#pragma unroll 1
-                                    for (int j = 0; j < nks; ++j) {
-                                        tmem_cp_128x256b<2>(ah + hb + 8 * j, sd + (uint64_t)((32 * j) >> 4));
-                                        tmem_cp_128x256b<2>(al + hb + 8 * j, sd + (uint64_t)((IMG + 32 * j) >> 4));
-                                    }
                                     const uint64_t wb = w_desc + (uint64_t)((a.w_off[0] + b * 2 * HIMG) >> 4);
 #pragma unroll 1
                                     for (int j = 0; j < nks; ++j) {
@@ -335,7 +389,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) row_pair_kern
                                         umma_ts<2>(d_col, al + hb + 8 * j, wh, idesc, 1u);
                                         umma_ts<2>(d_col, ah + hb + 8 * j, wl, idesc, 1u);
                                     }
-                                    umma_commit<2>(&s.empty[st], 3);
+                                    // this half may be refilled once these MMAs are done -- unless it is its last use in the tile and
+                                    // later layers keep their A operand in the same columns: then it is released after the last layer
+                                    if (nl == 1 || b + 2 < NKB) umma_commit<2>(&s.empty[buf], 3);
                                 }
                             }
                             if (lane == 0) umma_commit<2>(&s.d_full[c], 3);
@@ -356,6 +412,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) row_pair_kern
                                     umma_ts<2>(d_col, ah + 8 * ks, wl, id, 1u);
                                 }
                                 umma_commit<2>(&s.d_full[c], 3);
+                                if (l == nl - 1) {         // the chain's A operand columns are free for the next tile's K-blocks
+                                    umma_commit<2>(&s.empty[2 * c], 3);
+                                    if (NKB >= 2) umma_commit<2>(&s.empty[2 * c + 1], 3);
+                                }
                             }
                             ++n_ar[c];
                         }
@@ -400,12 +460,9 @@ int row_pair_launch(const G4cRowTcDesc& d, cudaStream_t st) {
     a.w_bytes = off;
     a.ring_off = (off + 1023u) & ~1023u;
     const uint32_t tail = (uint32_t)sizeof(rp::Tail);
-    const int avail = pairk::kMaxSmem - (int)a.ring_off - (int)tail - 16;
-    a.n_stage = std::min(4, avail / rp::STAGE);
-    if (a.n_stage < 2) { set_error("g4c_rowmlp_tc_fwd: weights (%u bytes per CTA) leave no room for the input ring", off); return G4C_EUNSUPPORTED; }
-    a.tail_off = a.ring_off + (uint32_t)a.n_stage * rp::STAGE;
-    a.tail_off = (a.tail_off + 15u) & ~15u;
+    a.tail_off = (a.ring_off + (uint32_t)rp::RING_BYTES + 15u) & ~15u;
     const int smem = (int)(a.tail_off + tail);
+    if (smem > pairk::kMaxSmem) { set_error("g4c_rowmlp_tc_fwd: weights (%u bytes per CTA) leave no room for the input rings", off); return G4C_EUNSUPPORTED; }
     const int64_t n_pt = (d.rows + 255) / 256;
     a.n_pt = n_pt;
     static int configured_smem = 0;

@@ -106,7 +106,7 @@ class MlpPack:
     def tc_row_ok(self, seg_widths) -> bool:
         return (self.hidden == 128 and sum(seg_widths) == self.in_width
                 and all(w == 128 or 1 <= w <= 16 for w in seg_widths)
-                and sum(2 if w == 128 else 1 for w in seg_widths) <= 6
+                and sum(2 if w == 128 else 1 for w in seg_widths) <= 5
                 and (self.out_width == 128 or (self.out_width < 16 and self.ln is None and self.n_layers > 1)))
 
     def tc_row(self, seg_widths) -> "RowPairPack":
