@@ -152,6 +152,7 @@ def run_g4c(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # stdout carries the one JSON line only
         dist.init_process_group("nccl", device_id=dev)
 
     g, params = build_workload(a, a.nodes)
