@@ -151,8 +151,12 @@ def run_g4c(a):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # stdout carries the ONE JSON line only: libraries write there too (NCCL prints its version banner on rank 0's
+    # stdout), so file descriptor 1 is pointed at stderr for the whole run and the line goes to the saved descriptor
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # stdout carries the one JSON line only
         dist.init_process_group("nccl", device_id=dev)
 
     g, params = build_workload(a, a.nodes)
@@ -253,7 +257,8 @@ def run_g4c(a):
                 "e2e": {"value": e2e_val, "unit": "steps/s", "h2d_bytes_per_step": N_local * fw * 4 * world,
                         "d2h_bytes_per_step": N_local * nf * 4 * world, "steps": e2e_steps},
                 "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cb}
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         # Tearing the NCCL communicator down while CUDA graphs that captured its kernels are alive can hang
         # (seen at N=2: the line above printed, then destroy_process_group never returned).  Every rank has
