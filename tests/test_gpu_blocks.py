@@ -131,3 +131,18 @@ def test_rejects_cpu_tensors_loudly():
     blk = g4.MLP(4, (16, 16), False)
     with pytest.raises(RuntimeError):
         blk(torch.randn(3, 4))
+
+
+@pytest.mark.parametrize("hidden", [64, 256])
+def test_mus_rollout_other_widths_vs_oracle(hidden):
+    """BASELINE.json configs[0] (hidden 64) and configs[4] (hidden 256): the exact-fp32 CUDA-core path."""
+    import graphs4cfd_b200 as g4
+    from graphs4cfd_b200 import mesh as M
+    from graphs4cfd_b200.archs import init_params, mus_arch
+    from oracle import restate as R
+    n = 2500
+    g = M.build_mus_mesh(n, 6, M.auto_cells(n, 3), seed=11)
+    params = init_params(mus_arch(hidden, 3), seed=5)
+    want = R.solve(params, g.clone(), 2)
+    got = g4.Rollout(params, g).solve(2).cpu()
+    assert rel_l2(got, want) <= 5e-5, rel_l2(got, want)

@@ -65,3 +65,19 @@ def test_remus_rollout_h128_vs_oracle(precision, tol):
     want = R.solve(params, g.clone(), 2)
     got = g4.Rollout(params, g, precision=precision).solve(2).cpu()
     assert rel_l2(got, want) <= tol, rel_l2(got, want)
+
+
+@pytest.mark.parametrize("hidden", [64, 256])
+def test_remus_rollout_other_widths_vs_oracle(hidden):
+    """configs[4] names hidden = 256: widths other than 128 run on the exact-fp32 CUDA-core kernels (precision 'auto')."""
+    import graphs4cfd_b200 as g4
+    from graphs4cfd_b200 import mesh as M
+    from graphs4cfd_b200.archs import init_params, remus_arch
+    from oracle import restate as R
+    g = M.build_remus_mesh(900, 6, seed=7)
+    params = init_params(remus_arch(hidden), seed=4)
+    want = R.solve(params, g.clone(), 2)
+    eng = g4.Rollout(params, g)
+    assert eng.precision == "fp32"
+    got = eng.solve(2).cpu()
+    assert rel_l2(got, want) <= 5e-5, rel_l2(got, want)
