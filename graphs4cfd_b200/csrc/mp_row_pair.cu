@@ -382,7 +382,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) row_pair_kern
                                     mbar_wait_sleep(&s.full[buf], upar);
                                     tc_fence_after();
                                     const uint64_t wb = w_desc + (uint64_t)((a.w_off[0] + b * 2 * HIMG) >> 4);
-#pragma unroll 1
+#pragma unroll 4
                                     for (int j = 0; j < nks; ++j) {
                                         const uint64_t wh = wb + (uint64_t)((32 * j) >> 4), wl = wh + (uint64_t)(HIMG >> 4);
                                         umma_ts<2>(d_col, ah + hb + 8 * j, wh, idesc, (b > 0 || j > 0) ? 1u : 0u);
@@ -403,8 +403,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) row_pair_kern
                                 const uint32_t kb_bytes = narrow_layer ? 4096u : 2u * HIMG, lo_off = narrow_layer ? 2048u : (uint32_t)HIMG;
                                 const uint64_t wb = w_desc + (uint64_t)(a.w_off[l] >> 4);
                                 const uint32_t id = narrow_layer ? idesc_narrow : idesc;
-#pragma unroll 1
-                                for (int ks = 0; ks < 8; ++ks) {
+#pragma unroll
+                                for (int ks = 0; ks < 8; ++ks) {     // straight-line issue: the rolled loop costs the single issuing thread ~110 cycles per MMA (64 at the pipe's rate)
                                     const uint64_t wh = wb + (uint64_t)(((ks >> 2) * kb_bytes + (ks & 3) * 32) >> 4);
                                     const uint64_t wl = wh + (uint64_t)(lo_off >> 4);
                                     umma_ts<2>(d_col, ah + 8 * ks, wh, id, ks > 0 ? 1u : 0u);
