@@ -581,7 +581,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_pair_ker
                                 }
                                 ++n_ar[c];
                             }
-                            if (lane == 0) {
+                            if (elect_one()) {
                                 const uint64_t wb = w_desc + (uint64_t)((l * 4 * HIMG) >> 4);
 #pragma unroll 1
                                 for (int ks = 0; ks < 8; ++ks) {

@@ -60,6 +60,15 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) { mbar_arrive_remote(cluster_addr); }
 
+// One elected lane of a converged warp.  Code under `if (elect_one())` is compiled for the uniform datapath: the MMA issue
+// loop becomes three back-to-back UTCHMMA per K step with uniform-register descriptor arithmetic, where `if (lane == 0)`
+// costs ~100 vector instructions and a lane loop per K step (the issuing thread then needs ~110 cycles per MMA).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t p;
+    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}\n" : "=r"(p));
+    return p != 0;
+}
+
 // ------------------------------------------------------------------ bounded waits
 // plain (cta-scope acquire) try_wait: the data handed over through these barriers lives in TMEM or was written by
 // the async proxy, and is ordered by tcgen05 fences / complete_tx; a .acquire.cluster wait would add a CCTL.IVALL
