@@ -331,8 +331,8 @@ def roofline_mp(eng, a, dev, ms_per_step):
                             "frac": 3 * flops / (dur_ms * 1e-3) / 1e12 / peaks.get("bf16_tflops", 1590.0),
                             "note": "fp16x3: every product is issued as 3 fp16 MMAs with fp32 accumulation"}}
         share = len(lvl1) * dur_ms / ms_per_step
-        # ncu --set full capture of this launch (profiles/r1e_edge_pair_v3_ncu.txt): dram read + write bytes
-        traffic = 7.965e9 if (E, N, H) == (6_000_000, 1_000_000, 128) else None
+        # ncu --set full capture of this launch (profiles/r1h_edge_pair_v3_ncu.txt): dram read + write bytes
+        traffic = 8.055e9 if (E, N, H) == (6_000_000, 1_000_000, 128) else None
     else:
         def launch():
             ops.mp(arg["ep"], arg["np_"], topo, arg["e_in"], arg["v_in"], arg["v_in"], act_e="selu", act_t="selu",
