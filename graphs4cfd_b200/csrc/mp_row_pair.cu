@@ -377,10 +377,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) row_pair_kern
                                 const uint32_t upar = (ubits >> buf) & 1u;
                                 ubits ^= 1u << buf;
                                 if (lane == 0) {
-                                    const int nks = a.kb[b].width == 64 ? 4 : 1;
-                                    const uint32_t hb = 32u * (b & 1);
                                     mbar_wait_sleep(&s.full[buf], upar);
                                     tc_fence_after();
+                                }
+                                if (elect_one()) {           // uniform-datapath issue loop (see elect_one in tc2_core.cuh)
+                                    const int nks = a.kb[b].width == 64 ? 4 : 1;
+                                    const uint32_t hb = 32u * (b & 1);
                                     const uint64_t wb = w_desc + (uint64_t)((a.w_off[0] + b * 2 * HIMG) >> 4);
 #pragma unroll 4
                                     for (int j = 0; j < nks; ++j) {
@@ -399,6 +401,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) row_pair_kern
                             if (lane == 0) {
                                 mbar_wait_sleep(&s.a_ready[c], n_ar[c] & 1);
                                 tc_fence_after();
+                            }
+                            if (elect_one()) {
                                 // K = 128 from the A operand the epilogue wrote; 64-row images, or 16-row images (N = 32)
                                 const uint32_t kb_bytes = narrow_layer ? 4096u : 2u * HIMG, lo_off = narrow_layer ? 2048u : (uint32_t)HIMG;
                                 const uint64_t wb = w_desc + (uint64_t)(a.w_off[l] >> 4);
