@@ -239,7 +239,9 @@ typedef struct {
  * P_r, P_c of the split edge model).  Segments are 128 wide (two 64-wide K-blocks) or at most 16 wide (one
  * K-block, zero padded).  W[0] = pair images of linear_1 with its columns laid out K-block by K-block
  * ([128, 64*n_kblocks], narrow segments padded to 64 columns); W[l] = pair images of the later layers; when
- * out_width < 16 the last layer's rows are padded to 32 and stored as 16-row images (ops.pack_weight_pair with 32 rows). */
+ * out_width < 16 the last layer's rows are padded to 32 and stored as 16-row images (ops.pack_weight_pair with 32 rows).
+ * At most 5 K-blocks in total (the resident weights plus the loaders' row rings must fit in 227 KiB of shared memory);
+ * wide segments must be 16-byte aligned with a row stride that is a multiple of 4 floats. */
 typedef struct {
     int64_t rows;
     int32_t n_segs;                   /* 1..3                                                  */
