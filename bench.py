@@ -160,9 +160,12 @@ def run_g4c(a):
         dist.init_process_group("nccl", device_id=dev)
 
     g, params = build_workload(a, a.nodes)
-    if world > 1 and a.model != "mus":
-        raise SystemExit("bench.py: --model remus runs on one GPU (the node-range partition covers the MuS-GNN models)")
-    if world > 1:
+    if world > 1 and a.model == "remus":
+        # edge-halo partition (graphs4cfd_b200/partition_remus.py)
+        from graphs4cfd_b200.partition_remus import PartitionedRemusRollout
+        eng = PartitionedRemusRollout(params, g, rank=rank, world=world, precision=a.precision, device=dev,
+                                      cuda_graph=not a.no_graph)
+    elif world > 1:
         from graphs4cfd_b200.partition import PartitionedRollout
         eng = PartitionedRollout(params, g, rank=rank, world=world, precision=a.precision, device=dev,
                                  cuda_graph=not a.no_graph)

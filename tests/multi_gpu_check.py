@@ -1,4 +1,4 @@
-"""torchrun entry (one rank per GPU): PartitionedRollout vs the single-domain oracle and vs single-GPU Rollout.
+"""torchrun entry (one rank per GPU): PartitionedRollout (G4C_MODEL=remus: PartitionedRemusRollout) vs the single-domain oracle and vs single-GPU Rollout.
 Launched by tests/test_gpu_multi.py:  python -m torch.distributed.run --nproc-per-node N tests/multi_gpu_check.py"""
 import os
 import sys
@@ -22,11 +22,21 @@ def main():
     from oracle import restate as R
     precision = os.environ.get("G4C_PRECISION", "fp32")
     H = 128 if precision != "fp32" else 32
-    n, steps = 6000, 3
-    g = M.build_mus_mesh(n, 6, M.auto_cells(n, 3), seed=5)
-    params = init_params(mus_arch(H, 3), seed=2)
-    eng = PartitionedRollout(params, g, rank, world, precision=precision, device=dev,
-                             cuda_graph=os.environ.get("G4C_GRAPH", "0") == "1")
+    steps = 3
+    if os.environ.get("G4C_MODEL", "mus") == "remus":        # edge-halo partition of the REMuS-GNN (partition_remus.py)
+        from graphs4cfd_b200.archs import remus_arch
+        from graphs4cfd_b200.partition_remus import PartitionedRemusRollout
+        n = 4000
+        g = M.build_remus_mesh(n, 6, seed=5)
+        params = init_params(remus_arch(H), seed=2)
+        eng = PartitionedRemusRollout(params, g, rank, world, precision=precision, device=dev,
+                                      cuda_graph=os.environ.get("G4C_GRAPH", "0") == "1")
+    else:
+        n = 6000
+        g = M.build_mus_mesh(n, 6, M.auto_cells(n, 3), seed=5)
+        params = init_params(mus_arch(H, 3), seed=2)
+        eng = PartitionedRollout(params, g, rank, world, precision=precision, device=dev,
+                                 cuda_graph=os.environ.get("G4C_GRAPH", "0") == "1")
     out = eng.gather(eng.solve(steps), n).cpu()
     ok = True
     if rank == 0:
