@@ -218,6 +218,12 @@ int g4c_debug_profile(uint64_t* out64) {
     return edge_pair_profile(reinterpret_cast<unsigned long long*>(out64));
 }
 
+int g4c_debug_set_edge_mode(int32_t mode) {
+    if (mode < 0 || mode > 2) { set_error("g4c_debug_set_edge_mode: mode=%d (0..2)", mode); return G4C_EINVAL; }
+    edge_pair_set_mode(mode);
+    return G4C_OK;
+}
+
 int g4c_host_guillard(const int64_t* senders, int64_t n, int32_t k, uint8_t* coarse_mask) {
     if (!senders || !coarse_mask || n < 0 || k < 1) { set_error("g4c_host_guillard: bad arguments"); return G4C_EINVAL; }
     memset(coarse_mask, 1, (size_t)n);

@@ -624,6 +624,8 @@ int edge_pair_profile(unsigned long long* out64) {
 }
 
 int edge_pair_launch(const EdgeArgs& a, cudaStream_t st) {
+    const int mode = edge_pair_mode();          // 0 unless G4C_EDGE_MODE / g4c_debug_set_edge_mode asks for an experimental variant
+    if (mode > 0 && edge_pair_tma_supported(a)) return edge_pair_tma_launch(a, mode, st);
     if (a.act_e_out != G4C_ACT_NONE && a.act_e_out != G4C_ACT_SELU) {
         // the models only ever apply F.selu to a block's edge / angle output (nn/mus_gnn.py:321, nn/remus_gnn.py:143)
         set_error("g4c_edge_aggr_fwd: act_e_out must be none or selu");

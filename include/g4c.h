@@ -298,6 +298,12 @@ G4C_API int g4c_debug_tc2(int32_t test, const float* A, const void* W_pack, floa
 /* in-kernel phase profile of edge_pair_kernel (HOST pointer to 64 uint64; only in builds with -DG4C_PROFILE) */
 G4C_API int g4c_debug_profile(uint64_t* out64);
 
+/* EXPERIMENTAL: variant of the kernel behind g4c_edge_aggr_fwd for launches with fixed_k > 0 and no permutations
+ * (csrc/mp_edge_pair_tma.cu).  0 = default kernel; 1 = e' staged in shared memory and written by TMA tensor stores;
+ * 2 = 1 + e / P_c tiles read by TMA tensor loads.  Same result as mode 0.  The environment variable
+ * G4C_EDGE_MODE sets the initial value. */
+G4C_API int g4c_debug_set_edge_mode(int32_t mode);
+
 G4C_API int g4c_host_guillard(const int64_t* senders, int64_t n, int32_t k, uint8_t* coarse_mask);
 
 #ifdef __cplusplus

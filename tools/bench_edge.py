@@ -17,6 +17,8 @@ ap.add_argument("--spread", type=int, default=2000, help="sources are drawn with
 ap.add_argument("--layers", type=int, default=3)
 ap.add_argument("--no-e", action="store_true")
 ap.add_argument("--act", default="selu")
+ap.add_argument("--modes", default="0", help="comma-separated kernel variants to time (0 = default, 1 / 2 = experimental TMA data paths, "
+                                            "csrc/mp_edge_pair_tma.cu); the outputs of every variant are compared with the first one's")
 a = ap.parse_args()
 
 dev = torch.device("cuda")
@@ -41,22 +43,35 @@ def launch():
     ops.edge_aggr(pack, topo, e, P_r, P_c, act_e=(None if a.act == "none" else a.act), want_e=not a.no_e, e_out=e_out, agg_out=agg)
 
 
-for _ in range(3):
-    launch()
-torch.cuda.synchronize()
-ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-ev0.record()
-for _ in range(a.reps):
-    launch()
-ev1.record()
-torch.cuda.synchronize()
-ms = ev0.elapsed_time(ev1) / a.reps
 E = n * k
 alg = 4 * 128 * ((1 if a.no_e else 2) * E + 3 * n) + 4 * E
 flop = 2 * E * 128 * 128 * a.layers
-print(f"edge_pair_kernel: N={n} E={E} layers={a.layers} write_e={not a.no_e}: {ms:.3f} ms/launch, "
-      f"{alg / ms / 1e6:.1f} GB/s algorithmic ({alg / 1e9:.2f} GB), {flop / ms / 1e9:.1f} TFLOP/s useful "
-      f"({3 * flop / ms / 1e9:.1f} issued fp16)")
+first = None
+for mode in [int(m) for m in a.modes.split(",")]:
+    ops.L.check(ops.L.lib().g4c_debug_set_edge_mode(mode))
+    e_out.fill_(float("nan"))
+    agg.fill_(float("nan"))
+    for _ in range(3):
+        launch()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(a.reps):
+        launch()
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / a.reps
+    same = ""
+    if first is None:
+        first = (agg.clone(), None if a.no_e else e_out.clone())
+    else:
+        same = f"; agg equal to mode {a.modes.split(',')[0]}: {torch.equal(agg, first[0])}"
+        if not a.no_e:
+            same += f", e' equal: {torch.equal(e_out, first[1])}"
+    print(f"edge kernel mode {mode}: N={n} E={E} layers={a.layers} write_e={not a.no_e}: {ms:.3f} ms/launch, "
+          f"{alg / ms / 1e6:.1f} GB/s algorithmic ({alg / 1e9:.2f} GB), {flop / ms / 1e9:.1f} TFLOP/s useful "
+          f"({3 * flop / ms / 1e9:.1f} issued fp16){same}")
+ops.L.check(ops.L.lib().g4c_debug_set_edge_mode(0))
 
 if os.environ.get("G4C_PROFILE"):
     import ctypes as C
