@@ -302,10 +302,14 @@ class _CudaBackend:
     def project(self, V, level, extras, out):
         from . import ops
         col, U = self.eng.col1[level], self.eng.U[level]
+        if col.numel() == 0:              # this rank owns no node of the level: nothing to launch
+            return
         self.steps.append(lambda: ops.project(V, col, U, extras, out=out))
 
     def rowmlp(self, prefix, segs, act, out, rows):
         from . import ops
+        if rows == 0:
+            return
         pack = self.eng.pack(prefix)
         precision = "auto" if self.eng.precision == "fp16x3" else "fp32"      # "auto": tensor-core kernel where it supports the shape
         self.steps.append(lambda: ops.rowmlp(pack, segs, rows=rows, act=act, out=out, precision=precision))
@@ -325,6 +329,8 @@ class _CudaBackend:
         from . import ops
         eng = self.eng
         ep, npk, topo = eng.pack(name + ".angle_mlp"), eng.pack(name + ".edge_mlp"), eng.topos[key]
+        if topo.n_targets == 0:
+            return
         eng.mp_args.append(dict(ep=ep, np_=npk, topo=topo, e_in=a_in, s_in=s_in, v_in=t_in, e_out=a_out, v_out=t_out))
         ws = self._workspace(int(s_in.shape[0]), int(t_in.shape[0]))
         self.steps.append(lambda: ops.mp(ep, npk, topo, a_in, s_in, t_in, act_e="selu", act_t="selu",
@@ -333,11 +339,15 @@ class _CudaBackend:
     def edge_to_node(self, e, level, out, residual):
         from . import ops
         Uinv = self.eng.Uinv[level]
+        if Uinv.shape[0] == 0:
+            return
         self.steps.append(lambda: ops.edge_to_node(e, Uinv, out=out, residual=residual))
 
     def interp(self, v_lo, hi, vfull):
         from . import ops
         it = self.eng.interp[hi]
+        if it["n_y"] == 0:
+            return
         self.steps.append(lambda: ops.interp(v_lo, it["x_idx"], it["w"], it["k"], it["n_y"], vfull, it["y_row"]))
 
     def xchg(self, buf, x: Xchg):
