@@ -219,7 +219,7 @@ int g4c_debug_profile(uint64_t* out64) {
 }
 
 int g4c_debug_set_edge_mode(int32_t mode) {
-    if (mode < 0 || mode > 2) { set_error("g4c_debug_set_edge_mode: mode=%d (0..2)", mode); return G4C_EINVAL; }
+    if (mode < 0 || mode > 3) { set_error("g4c_debug_set_edge_mode: mode=%d (0..3)", mode); return G4C_EINVAL; }
     edge_pair_set_mode(mode);
     return G4C_OK;
 }

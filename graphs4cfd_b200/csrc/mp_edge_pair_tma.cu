@@ -1,6 +1,6 @@
 // mp_edge_pair_tma.cu — edge_pair_kernel (mp_edge_pair.cu, "v3") with bulk-tensor (TMA) data paths.  "v4".
 //
-// STATUS: EXPERIMENTAL and OPT-IN (G4C_EDGE_MODE=1|2 or g4c_debug_set_edge_mode): written after the round's GPU budget
+// STATUS: EXPERIMENTAL and OPT-IN (G4C_EDGE_MODE=1|2|3 or g4c_debug_set_edge_mode): written after the round's GPU budget
 // was spent; it compiles for sm_100a but has NOT run on hardware yet.  The default path is the v3 kernel, untouched.
 //
 // Why (profiles/r1d_edge_pair_v3_phases.txt): v3 is limited by the SM's load/store pipe, not by HBM
@@ -16,6 +16,8 @@
 //           the [N, k, 128] view of e; box 16 x 32 of P_c; SWIZZLE_64B = the ring's layout) signalled on a per-warp,
 //           per-stage mbarrier; only the gathered P_r[src] pieces stay on cp.async (4 of the 12 LDGSTS per stage, and
 //           none of the e / P_c address arithmetic).
+//   mode 3  additionally the gathered P_r[src] pieces arrive through TMA (tile::gather4: four source rows per copy, eight
+//           copies per stage issued by lanes 0-7 with their own row coordinates): no LDGSTS at all in the loaders.
 // Restrictions (checked by the launcher, which falls back to v3): fixed in-degree (fixed_k > 0), edges stored in
 // aggregation order (no edge_perm / tgt_perm).  That covers the level-1 kNN launches and every REMuS angle level,
 // i.e. the launches that dominate the step.  Arithmetic, TMEM layout, MMA issue, hidden epilogues and the LayerNorm
@@ -55,6 +57,7 @@ struct Maps {
     CUtensorMap e_in;                    // [N, k, 128] fp32, box 16 x 1 x 32, SWIZZLE_64B
     CUtensorMap p_c;                     // [N, 128] fp32, box 16 x 32, SWIZZLE_64B
     CUtensorMap e_out;                   // [N, k, 128] fp32, box 8 x 1 x 32, SWIZZLE_32B
+    CUtensorMap p_r;                     // [*, 128] fp32, box 16 x 1 (tile::gather4: four rows per copy), SWIZZLE_64B
 };
 
 struct Smem {
@@ -109,6 +112,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, 
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                  ::"r"(dst), "l"(m), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
+// four rows r0..r3 of a 2-D tensor, box_cols columns from c0 each, to four consecutive row pieces at dst
+__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* m, int c0, int r0, int r1, int r2, int r3, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+                 ::"r"(dst), "l"(m), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar) : "memory");
+}
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, int c0, int c1, int c2, uint32_t src) {
     asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];"
                  ::"l"(m), "r"(c0), "r"(c1), "r"(c2), "r"(src) : "memory");
@@ -117,8 +125,10 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 // every bulk group this thread committed has finished READING its shared-memory source
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
-template <bool kTmaLoad>
+// kLoad: 0 = every row piece by cp.async (mode 1), 1 = e / P_c tiles by TMA (mode 2), 2 = P_r[src] by TMA gather4 as well (mode 3)
+template <int kLoad>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_tma_kernel(const EdgeArgs a, const __grid_constant__ Maps tm) {
+    constexpr bool kTmaLoad = kLoad >= 1, kGather = kLoad == 2;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     Smem& s = *reinterpret_cast<Smem*>(smem_raw);
     if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
@@ -357,21 +367,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_tma_kern
         int64_t i_n = -1;                 // this lane's target in the unit pair being issued, -1: none
         int nx_srow = -1;
         uint32_t oe[4], os[4], ot[4], vmask = 0;
+        int gr[4] = {0, 0, 0, 0};         // kGather: lanes 0-7 hold the source rows of tile rows 4 lane .. 4 lane + 3
         bool i_live = false;
         auto load_src = [&](int j) -> int {               // source row of the j-th in-edge of this lane's target
             return (i_n >= 0 && j < k) ? __ldg(a.src + i_n * k + j) : -1;
         };
         auto spread_slot = [&](int j, int srow) {
             vmask = 0;
+            if (kGather) {
+                // a tile row without an edge reads row 0 of P_r: its accumulator row is never stored (rows are independent
+                // through the MMAs and the LayerNorm; agg is skipped and the e' store is clipped for it)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int sr = __shfl_sync(0xffffffffu, srow, 8 * i + sub);
-                const bool ok = sr >= 0;
-                vmask |= ok ? (1u << i) : 0u;
-                os[i] = ok ? (uint32_t)sr * 32u + piece : 0u;
-                if (!kTmaLoad) {
-                    const long long er = __shfl_sync(0xffffffffu, (long long)(i_n >= 0 ? i_n * k + j : -1), 8 * i + sub);
-                    oe[i] = ok ? (uint32_t)er * 32u + piece : 0u;
+                for (int i = 0; i < 4; ++i) gr[i] = max(__shfl_sync(0xffffffffu, srow, (4 * lane + i) & 31), 0);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int sr = __shfl_sync(0xffffffffu, srow, 8 * i + sub);
+                    const bool ok = sr >= 0;
+                    vmask |= ok ? (1u << i) : 0u;
+                    os[i] = ok ? (uint32_t)sr * 32u + piece : 0u;
+                    if (!kTmaLoad) {
+                        const long long er = __shfl_sync(0xffffffffu, (long long)(i_n >= 0 ? i_n * k + j : -1), 8 * i + sub);
+                        oe[i] = ok ? (uint32_t)er * 32u + piece : 0u;
+                    }
                 }
             }
         };
@@ -403,7 +421,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_tma_kern
                     sz[i] = (vmask >> i) & 1u ? 16u : 0u;
                     pr[i] = reinterpret_cast<const float*>(br + (size_t)os[i] * 16);
                 }
-                if (kTmaLoad) {
+                if (kGather) {
+                    const int n0w = (i_up * 2 + (int)rank) * 128 + lw * 32;
+                    if (leader) {
+                        mbar_arrive_expect_tx_a(bar_addr, 3 * ARR);
+                        tma_load_3d(stage_addr, &tm.e_in, col0, i_j, n0w, bar_addr);
+                        tma_load_2d(stage_addr + 2 * ARR, &tm.p_c, col0, n0w, bar_addr);
+                    }
+                    __syncwarp();
+                    // eight copies of four gathered rows each; divergent operands: ptxas serialises the lanes (R2UR + BRA.U.ANY)
+                    if (lane < 8) tma_gather4(stage_addr + ARR + 256u * lane, &tm.p_r, col0, gr[0], gr[1], gr[2], gr[3], bar_addr);
+                } else if (kTmaLoad) {
                     asm volatile(
                         "cp.async.cg.shared.global [%0 + 2048], [%1], 16, %5;\n\t"
                         "cp.async.cg.shared.global [%0 + 2560], [%2], 16, %6;\n\t"
@@ -590,8 +618,8 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// fp32 view [rows, (k,) 128] of a row-major feature matrix; box = box_cols x (1 x) 32 rows
-static bool encode(CUtensorMap* m, const float* base, int64_t rows, int k, int box_cols, CUtensorMapSwizzle swz) {
+// fp32 view [rows, (k,) 128] of a row-major feature matrix; box = box_cols x (1 x) box_rows
+static bool encode(CUtensorMap* m, const float* base, int64_t rows, int k, int box_cols, CUtensorMapSwizzle swz, int box_rows = 32) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
     const cuuint32_t ones[3] = {1, 1, 1};
@@ -599,13 +627,13 @@ static bool encode(CUtensorMap* m, const float* base, int64_t rows, int k, int b
     if (k > 0) {
         const cuuint64_t dims[3] = {128, (cuuint64_t)k, (cuuint64_t)rows};
         const cuuint64_t strides[2] = {512, (cuuint64_t)512 * k};
-        const cuuint32_t box[3] = {(cuuint32_t)box_cols, 1, 32};
+        const cuuint32_t box[3] = {(cuuint32_t)box_cols, 1, (cuuint32_t)box_rows};
         r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     } else {
         const cuuint64_t dims[2] = {128, (cuuint64_t)rows};
         const cuuint64_t strides[1] = {512};
-        const cuuint32_t box[2] = {(cuuint32_t)box_cols, 32};
+        const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
         r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     }
@@ -622,7 +650,7 @@ int edge_pair_mode() {
     if (g_edge_mode < 0) {
         const char* e = std::getenv("G4C_EDGE_MODE");
         g_edge_mode = e ? std::atoi(e) : 0;
-        if (g_edge_mode < 0 || g_edge_mode > 2) g_edge_mode = 0;
+        if (g_edge_mode < 0 || g_edge_mode > 3) g_edge_mode = 0;
     }
     return g_edge_mode;
 }
@@ -637,13 +665,17 @@ int edge_pair_tma_launch(const EdgeArgs& a, int mode, cudaStream_t st) {
     ep4::Maps tm;
     bool ok = ep4::encode(&tm.e_in, a.e_in, a.n_targets, a.fixed_k, 16, CU_TENSOR_MAP_SWIZZLE_64B) &&
               ep4::encode(&tm.p_c, a.P_c, a.n_targets, 0, 16, CU_TENSOR_MAP_SWIZZLE_64B) &&
-              ep4::encode(&tm.e_out, a.e_out ? a.e_out : a.e_in, a.n_targets, a.fixed_k, 8, CU_TENSOR_MAP_SWIZZLE_32B);
+              ep4::encode(&tm.e_out, a.e_out ? a.e_out : a.e_in, a.n_targets, a.fixed_k, 8, CU_TENSOR_MAP_SWIZZLE_32B) &&
+              // tile::gather4 map: one-row box, four row coordinates per copy.  The descriptor does not carry the number of source
+              // rows (G4cEdgeDesc has no such field); the bound only matters for out-of-range coordinates, which are never issued.
+              ep4::encode(&tm.p_r, a.P_r, (int64_t)1 << 28, 0, 16, CU_TENSOR_MAP_SWIZZLE_64B, 1);
     if (!ok) { set_error("edge_pair_tma_launch: cuTensorMapEncodeTiled failed"); return G4C_ECUDA; }
     static bool configured = false;
     const int smem = (int)sizeof(ep4::Smem);
     if (!configured) {
-        if (cudaFuncSetAttribute(ep4::edge_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
-            cudaFuncSetAttribute(ep4::edge_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+        if (cudaFuncSetAttribute(ep4::edge_tma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+            cudaFuncSetAttribute(ep4::edge_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+            cudaFuncSetAttribute(ep4::edge_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
             return check_launch("edge_tma_kernel attribute");
         configured = true;
     }
@@ -656,8 +688,9 @@ int edge_pair_tma_launch(const EdgeArgs& a, int mode, cudaStream_t st) {
     }
     const int64_t n_units = (a.n_targets + 127) / 128, n_up = (n_units + 1) / 2;
     const int pairs = (int)std::min<int64_t>(n_up, n_sm / 2);
-    if (mode >= 2) ep4::edge_tma_kernel<true><<<2 * pairs, ep4::NT, smem, st>>>(a, tm);
-    else ep4::edge_tma_kernel<false><<<2 * pairs, ep4::NT, smem, st>>>(a, tm);
+    if (mode >= 3) ep4::edge_tma_kernel<2><<<2 * pairs, ep4::NT, smem, st>>>(a, tm);
+    else if (mode == 2) ep4::edge_tma_kernel<1><<<2 * pairs, ep4::NT, smem, st>>>(a, tm);
+    else ep4::edge_tma_kernel<0><<<2 * pairs, ep4::NT, smem, st>>>(a, tm);
     count_launch();
     return check_launch("edge_tma_kernel");
 }
