@@ -107,7 +107,7 @@ def _set_mode(mode):
 
 @gpu
 @experimental
-@pytest.mark.parametrize("mode", [1, 2, 3])
+@pytest.mark.parametrize("mode", [1, 2, 3], ids=["mode1", "mode2", "mode3"])
 @pytest.mark.parametrize("n,k", [(1000, 6), (256, 5), (77, 6), (40000, 6), (128, 1), (129, 2)])
 @pytest.mark.parametrize("n_layers", [3, 2])
 @pytest.mark.parametrize("want_e", [True, False])

@@ -1,0 +1,16 @@
+#!/bin/bash
+# First GPU call of the next round (one B200):   gpurun --timeout 1500 -- 'bash tools/r2_first_call.sh'
+# 1. the GPU parity suite; 2. the experimental edge-kernel variants (csrc/mp_edge_pair_tma.cu), each in its own process
+# under a timeout so that a hang in one mode costs two minutes, not the call; 3. their timings next to the default kernel.
+# Everything is written to gpurun_out/r2_*.log.
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -8 > gpurun_out/r2_pytest.log
+for m in 1 2 3; do
+  G4C_TEST_EXPERIMENTAL=1 timeout 120 python -m pytest tests/test_gpu_edge_pair.py -m gpu -x -q -k "tma_modes and mode${m}" 2>&1 | tail -12 > gpurun_out/r2_experimental_mode${m}.log
+  echo "mode $m parity exit $?" >> gpurun_out/r2_experimental_mode${m}.log
+done
+for m in 1 2 3; do
+  timeout 120 python tools/bench_edge.py --modes 0,$m 2>&1 | tail -4 > gpurun_out/r2_bench_edge_mode${m}.log
+  timeout 120 python tools/bench_edge.py --modes 0,$m --layers 2 --k 6 2>&1 | tail -4 >> gpurun_out/r2_bench_edge_mode${m}.log
+done
+tail -n 20 gpurun_out/r2_*.log
