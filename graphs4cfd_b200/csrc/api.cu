@@ -215,6 +215,7 @@ int g4c_debug_tc2(int32_t test, const float* A, const void* W_pack, float w_inv_
 int g4c_debug_profile(uint64_t* out64) {
     if (!out64) { set_error("g4c_debug_profile: NULL pointer"); return G4C_EINVAL; }
     cudaDeviceSynchronize();
+    if (edge_pair_mode() > 0) return edge_pair_tma_profile(reinterpret_cast<unsigned long long*>(out64));
     return edge_pair_profile(reinterpret_cast<unsigned long long*>(out64));
 }
 

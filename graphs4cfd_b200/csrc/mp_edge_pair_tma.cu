@@ -77,6 +77,20 @@ struct Smem {
 static_assert(sizeof(Smem) <= 232448, "shared memory exceeds the 227 KiB opt-in limit");
 static_assert(offsetof(Smem, ring) % 2048 == 0 && offsetof(Smem, ostage) % 1024 == 0, "TMA tile alignment");
 
+// ---- optional in-kernel phase profile (make EXTRA=-DG4C_PROFILE), same laps as mp_edge_pair.cu; read back with g4c_debug_profile()
+#ifdef G4C_PROFILE
+__device__ unsigned long long g_prof[64];
+#define PROF_DECL unsigned int prof_t0 = 0; unsigned long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define PROF_START() prof_t0 = clock()
+#define PROF_LAP(i) do { const unsigned int t1 = clock(); prof_acc[i] += (unsigned int)(t1 - prof_t0); prof_t0 = t1; } while (0)
+#define PROF_FLUSH(base, cond) do { if (blockIdx.x == 0 && lane == 0 && (cond)) for (int i = 0; i < 8; ++i) atomicAdd(&g_prof[(base) + i], prof_acc[i]); } while (0)
+#else
+#define PROF_DECL
+#define PROF_START()
+#define PROF_LAP(i)
+#define PROF_FLUSH(base, cond)
+#endif
+
 template <int N>
 __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N>
@@ -194,6 +208,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_tma_kern
         uint32_t n_dfull[2] = {0, 0};
         const bool has_ln = a.gamma != nullptr;
         int pbuf = 0;
+        PROF_DECL
+        PROF_START();
 
         for (int up = up0; up < n_up; up += up_stride) {
             const int n_unit0 = (up * 2 + (int)rank) * 128;         // n_targets < 2^31 (checked by g4c_edge_aggr_fwd)
@@ -214,6 +230,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_tma_kern
                         ++n_dfull[c];
                         epi_sync_all();
                         tc_fence_after();
+                        PROF_LAP(l < nl - 1 ? 0 : 1);        // waiting for the MMAs (hidden / last layer)
                         if (l < nl - 1) {
                             const float c2 = cl * kLog2e;
 #pragma unroll
@@ -239,6 +256,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_tma_kern
                             tc_fence_before();
                             __syncwarp();
                             if (lane == 0) mbar_arrive_remote(leader_a_ready0 + 8u * c);
+                            PROF_LAP(2);                     // hidden epilogue
                         } else {
                             const uint32_t bs = my_cst + 512u * l;
                             float y[32];
@@ -278,7 +296,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_tma_kern
                                 const uint32_t pa = my_part + 4096u * pbuf;
                                 sts_f1(pa + 512u * cq, 0.5f * (mh[0] + mh[1]));
                                 sts_f1(pa + 2048u + 512u * cq, (M2h[0] + M2h[1]) + 8.f * dm * dm);
+                                PROF_LAP(3);                 // last layer: read + statistics
                                 quarter_sync(lq);
+                                PROF_LAP(4);                 // last layer: barrier
                                 const float m0 = lds_f1(pa), m1 = lds_f1(pa + 512u), m2 = lds_f1(pa + 1024u), m3 = lds_f1(pa + 1536u);
                                 mean = 0.25f * ((m0 + m1) + (m2 + m3));
                                 const float d0 = m0 - mean, d1 = m1 - mean, d2 = m2 - mean, d3 = m3 - mean;
@@ -329,6 +349,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_tma_kern
                                     }
                                 }
                             }
+                            PROF_LAP(5);                     // last layer: normalise, aggregate, stage + bulk store
                         }
                     }
                 }
@@ -344,7 +365,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_tma_kern
                     stg256(dst + i, o);
                 }
             }
+            PROF_LAP(6);
         }
+        PROF_FLUSH(0, warp == 0);
     } else if (warp < W_LOAD0 + N_LOAD_WARPS) {
         // ====================================================================== loader warps
         setmaxnreg_dec<kRegsLoad>();
@@ -487,6 +510,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_tma_kern
         seek_unit();
 #pragma unroll 1
         for (int p = 0; p < NSTG - 1; ++p) issue_stage(ring0 + p * STG, bar0 + 8u * p);
+        PROF_DECL
+        PROF_START();
         uint32_t q = 0, n_slot0 = 0, n_slot1 = 0;
         const uint32_t swz = (uint32_t)((lane >> 1) & 3);
         for (int up = up0; up < n_up; up += up_stride) {
@@ -499,10 +524,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_tma_kern
                     cp_async_wait<NSTG - 2>();                   // the cp.async part of stage q has landed
                     if (kTmaLoad) mbar_wait_sleep_a(bar0 + 8u * (q % NSTG), (q / NSTG) & 1);      // ... and its two TMA tiles
                     __syncwarp();
+                    PROF_LAP(0);                                 // waiting for the staged rows
                     issue_stage(ring0 + ((q + NSTG - 1) % NSTG) * STG, bar0 + 8u * ((q + NSTG - 1) % NSTG));
                     if (cw == 0) {
                         mbar_wait_sleep_a(a_d_free + 8u * cc, ((cc ? n_slot1 : n_slot0) + 1) & 1);
                         tc_fence_after();
+                        PROF_LAP(1);                             // waiting for the accumulator to be released
                     }
                     const uint32_t st = ring0 + (q % NSTG) * STG + lane * 64;
 #pragma unroll
@@ -538,10 +565,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_tma_kern
                         if (lane == 0) mbar_arrive_remote(leader_in_ready0 + 8u * cc);
                         if (cc) ++n_slot1; else ++n_slot0;
                     }
+                    PROF_LAP(2);                                 // read back, split / add, TMEM writes, next prefetch
                 }
             }
         }
         cp_async_wait<0>();
+        PROF_FLUSH(8, warp == W_LOAD0);
     } else {
         setmaxnreg_dec<kRegsMisc>();
         if (warp == W_MMA && rank == 0) {
@@ -641,6 +670,19 @@ static bool encode(CUtensorMap* m, const float* base, int64_t rows, int k, int b
 }
 
 }  // namespace ep4
+
+int edge_pair_tma_profile(unsigned long long* out64) {
+#ifdef G4C_PROFILE
+    if (cudaMemcpyFromSymbol(out64, ep4::g_prof, sizeof(unsigned long long) * 64) != cudaSuccess) return check_launch("profile read");
+    unsigned long long zero[64] = {0};
+    cudaMemcpyToSymbol(ep4::g_prof, zero, sizeof(zero));
+    return G4C_OK;
+#else
+    (void)out64;
+    set_error("libg4c was built without -DG4C_PROFILE");
+    return G4C_EUNSUPPORTED;
+#endif
+}
 
 static int g_edge_mode = -1;      // -1: read G4C_EDGE_MODE on first use
 

@@ -19,5 +19,6 @@ int edge_pair_mode();
 void edge_pair_set_mode(int mode);
 bool edge_pair_tma_supported(const EdgeArgs& a);
 int edge_pair_tma_launch(const EdgeArgs& a, int mode, cudaStream_t st);
+int edge_pair_tma_profile(unsigned long long* out64);         // phase profile of the TMA variants (needs -DG4C_PROFILE)
 
 }  // namespace g4c
