@@ -78,9 +78,13 @@ if os.environ.get("G4C_PROFILE"):
     import numpy as np
     from graphs4cfd_b200 import _lib as L
     buf = np.zeros(64, dtype=np.uint64)
+    prof_mode = int(a.modes.split(",")[-1])                          # the last variant of --modes is the one profiled
+    L.check(L.lib().g4c_debug_set_edge_mode(prof_mode))
     L.lib().g4c_debug_profile(buf.ctypes.data_as(C.c_void_p))        # drop warm-up + timing launches
     launch()
     L.check(L.lib().g4c_debug_profile(buf.ctypes.data_as(C.c_void_p)))
+    L.check(L.lib().g4c_debug_set_edge_mode(0))
+    print(f"phase profile of mode {prof_mode} (the MMA issuer has no laps in the TMA variants):")
     names = {0: ("epilogue warp 0", ["wait MMA (hidden)", "wait MMA (last)", "hidden epilogue", "last: statistics", "last: barrier", "last: normalise+agg+store", "unit end", "-"]),
              8: ("loader warp 16", ["wait rows", "wait acc release", "process + prefetch", "-", "-", "-", "-", "-"]),
              16: ("MMA issuer", ["wait loaders", "wait epilogue", "issue", "-", "-", "-", "-", "-"])}
