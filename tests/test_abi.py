@@ -40,7 +40,7 @@ def test_ctypes_struct_sizes_match_header(built_lib, tmp_path):
              "G4cMpDesc": built_lib.MpDesc, "G4cSegReduceDesc": built_lib.SegReduceDesc,
              "G4cProjectDesc": built_lib.ProjectDesc, "G4cEdgeToNodeDesc": built_lib.EdgeToNodeDesc,
              "G4cInterpDesc": built_lib.InterpDesc, "G4cStepUpdateDesc": built_lib.StepUpdateDesc,
-             "G4cHaloDesc": built_lib.HaloDesc}
+             "G4cHaloDesc": built_lib.HaloDesc, "G4cEdgeDesc": built_lib.EdgeDesc, "G4cRowTcDesc": built_lib.RowTcDesc}
     src = tmp_path / "sz.c"
     body = "".join(f'printf("{n} %zu\\n", sizeof({n}));' for n in pairs)
     src.write_text(f'#include <stdio.h>\n#include "g4c.h"\nint main(void){{{body}return 0;}}\n')
@@ -50,6 +50,30 @@ def test_ctypes_struct_sizes_match_header(built_lib, tmp_path):
     for line in out.strip().splitlines():
         name, size = line.split()
         assert ctypes.sizeof(pairs[name]) == int(size), name
+
+
+def test_ctypes_field_offsets_match_header(built_lib, tmp_path):
+    """Every field of every descriptor sits at the offset the C compiler gives it (same names on both sides)."""
+    pairs = {"G4cMlp": built_lib.Mlp, "G4cSeg": built_lib.Seg, "G4cRowMlpDesc": built_lib.RowMlpDesc,
+             "G4cMpDesc": built_lib.MpDesc, "G4cEdgeDesc": built_lib.EdgeDesc, "G4cRowTcDesc": built_lib.RowTcDesc,
+             "G4cSegReduceDesc": built_lib.SegReduceDesc, "G4cProjectDesc": built_lib.ProjectDesc,
+             "G4cEdgeToNodeDesc": built_lib.EdgeToNodeDesc, "G4cInterpDesc": built_lib.InterpDesc,
+             "G4cStepUpdateDesc": built_lib.StepUpdateDesc, "G4cHaloDesc": built_lib.HaloDesc}
+    lines = []
+    for cname, cls in pairs.items():
+        for fname, *_ in cls._fields_:
+            lines.append(f'printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    src = tmp_path / "off.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "g4c.h"\nint main(void){' + "".join(lines) + "return 0;}\n")
+    exe = tmp_path / "off"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    n = 0
+    for line in out.strip().splitlines():
+        cname, fname, off = line.split()
+        assert getattr(pairs[cname], fname).offset == int(off), (cname, fname)
+        n += 1
+    assert n == len(lines)
 
 
 def test_host_plan_helper_matches_python_loop(built_lib):
