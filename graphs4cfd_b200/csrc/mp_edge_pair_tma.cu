@@ -322,27 +322,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_tma_kern
                                         o[u + 3] = fmaf((o[u + 3] - mean) * rstd, g.w, be.w);
                                     }
                                 }
-                                if (a.e_out != nullptr) {
-                                    // the staging tile is free once the previous piece's bulk store has read it
-                                    if (lane == 0) bulk_wait_read0();
-                                    __syncwarp();
-                                }
                                 if (live) {
 #pragma unroll
                                     for (int u = 0; u < 8; ++u) agg[i8 + u] += o[u];
-                                    if (a.e_out != nullptr) {
-                                        if (a.act_e_out == G4C_ACT_SELU) {
-#pragma unroll
-                                            for (int u = 0; u < 8; ++u) o[u] = selu_fast(o[u]);
-                                        }
-                                        sts_f4(ost0, o[0], o[1], o[2], o[3]);
-                                        sts_f4(ost0 ^ 16u, o[4], o[5], o[6], o[7]);
-                                    }
                                 }
-                                if (a.e_out != nullptr) {
+                                if (a.e_out != nullptr) {       // warp-uniform
+                                    if (a.act_e_out == G4C_ACT_SELU) {
+#pragma unroll
+                                        for (int u = 0; u < 8; ++u) o[u] = selu_fast(o[u]);
+                                    }
+                                    // the staging tile is free once the previous piece's bulk store has read it; everything above
+                                    // (normalise, aggregate, SELU of this piece) ran while the TMA engine was reading
+                                    if (lane == 0) bulk_wait_read0();
+                                    __syncwarp();
+                                    sts_f4(ost0, o[0], o[1], o[2], o[3]);
+                                    sts_f4(ost0 ^ 16u, o[4], o[5], o[6], o[7]);
                                     fence_proxy_async();        // generic-proxy writes -> visible to the TMA engine
                                     __syncwarp();
-                                    // rows past the last target hold stale bytes in the staging tile; the tensor map's bounds clip them
+                                    // rows past the last target hold values of no edge; the tensor map's bounds clip them
                                     if (lane == 0) {
                                         tma_store_3d(&tm.e_out, cq * 32 + i8, j, n_unit0 + lq * 32, ost0 & ~1023u);
                                         bulk_commit();
