@@ -114,6 +114,20 @@ __device__ __forceinline__ float selu_over_lambda_l2(float t) {
     return t > 0.f ? t * kLn2 : neg;
 }
 
+// Sleeping mbarrier wait with a tighter watchdog than tc2_core.cuh's (2^24 polls x 20 us): a protocol error in this
+// not-yet-run kernel traps after about five seconds instead of minutes.  Hides tc2::mbar_wait_sleep_a inside this namespace.
+__device__ __forceinline__ void mbar_wait_sleep_a(uint32_t addr, uint32_t parity) {
+    uint32_t spins = 0, ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(ok) : "r"(addr), "r"(parity), "r"(20000u) : "memory");
+        if (!ok && ++spins > (1u << 18)) __trap();
+    } while (!ok);
+}
+
 // ------------------------------------------------------------------ bulk-tensor copies (one thread issues)
 __device__ __forceinline__ void mbar_arrive_expect_tx_a(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
