@@ -98,20 +98,36 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--nodes", type=int, default=6000)
     ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--model", default="mus", choices=["mus", "remus"])
     a = ap.parse_args()
     torch.set_num_threads(os.cpu_count())
-    g = M.build_mus_mesh(a.nodes, 6, M.auto_cells(a.nodes, 3), seed=0)
     weights = "seeded default init"
-    params = init_params(mus_arch(128, 3), seed=0)
-    if os.path.isdir("/root/reference/graphs4cfd"):
+    have_ref = os.path.isdir("/root/reference/graphs4cfd")
+    if have_ref:
         from oracle.pyg_stub import import_reference
         gfd = import_reference()
-        model = gfd.nn.NsThreeScaleGNN(model="3S-GNN-NsCircle-v1")
-        params = {k: v.detach() for k, v in model.state_dict().items()}
-        weights = "shipped 3S-GNN-NsCircle-v1 checkpoint"
-    print(f"3-scale MuS-GNN, hidden 128, {a.nodes}-node synthetic mesh, {weights}; rel-L2 of the prediction vs the fp32 oracle")
+    if a.model == "remus":
+        from graphs4cfd_b200.archs import remus_arch
+        g = M.build_remus_mesh(a.nodes, 5, seed=0, points="uniform")       # k = 5: the shipped checkpoint's training setup
+        params = init_params(remus_arch(128), seed=0)
+        if have_ref:
+            model = gfd.nn.NsRotEquiTreeScaleGNN(model="RE3S-GNN-NsEllipse-v1")
+            params = {k: v.detach() for k, v in model.state_dict().items()}
+            weights = "shipped RE3S-GNN-NsEllipse-v1 checkpoint"
+        name = "3-scale REMuS-GNN"
+    else:
+        g = M.build_mus_mesh(a.nodes, 6, M.auto_cells(a.nodes, 3), seed=0)
+        params = init_params(mus_arch(128, 3), seed=0)
+        if have_ref:
+            model = gfd.nn.NsThreeScaleGNN(model="3S-GNN-NsCircle-v1")
+            params = {k: v.detach() for k, v in model.state_dict().items()}
+            weights = "shipped 3S-GNN-NsCircle-v1 checkpoint"
+        name = "3-scale MuS-GNN"
+    print(f"{name}, hidden 128, {a.nodes}-node synthetic mesh, {weights}; rel-L2 of the prediction vs the fp32 oracle")
     ref = rollout(params, g.clone(), a.steps)
-    runs = {"fp32, in-edges re-ordered (noise floor)": rollout(params, permute_in_edges(g, 1), a.steps)}
+    runs = {}
+    if a.model == "mus":       # (the REMuS angle layout is positional, transforms/remus.py:36-38: no free re-ordering)
+        runs["fp32, in-edges re-ordered (noise floor)"] = rollout(params, permute_in_edges(g, 1), a.steps)
     for kind in ("fp16x3", "tf32", "bf16"):
         with patched_linear(make_linear(kind)):
             runs[f"{kind} operands, fp32 accumulate"] = rollout(params, g.clone(), a.steps)
