@@ -36,7 +36,9 @@ def parse():
     ap.add_argument("--levels", type=int, default=3)
     ap.add_argument("--model", default="mus", choices=["mus", "remus"],
                     help="mus: the MuS-GNN workload of BASELINE.json's metric (default); remus: the 3-scale REMuS-GNN of "
-                         "configs[2] (single GPU only; a measurement case, not the driver's bench line)")
+                         "configs[2] (a measurement case, not the driver's bench line; N > 1 uses the edge-halo partition)")
+    ap.add_argument("--edge-mode", type=int, default=int(os.environ.get("G4C_EDGE_MODE", "0")),
+                    help="0 (default): the measured edge kernel; 1..3: experimental TMA variants (csrc/mp_edge_pair_tma.cu)")
     ap.add_argument("--precision", default=os.environ.get("G4C_PRECISION", "auto"),
                     help="auto (fp16x3 tensor-core path when hidden=128, else fp32) | fp16x3 | fp32")
     ap.add_argument("--no-graph", action="store_true")
@@ -159,6 +161,8 @@ def run_g4c(a):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    if a.edge_mode:
+        ops.L.check(ops.L.lib().g4c_debug_set_edge_mode(a.edge_mode))
     g, params = build_workload(a, a.nodes)
     if world > 1 and a.model == "remus":
         # edge-halo partition (graphs4cfd_b200/partition_remus.py)
@@ -253,6 +257,7 @@ def run_g4c(a):
                 "config": {"workload": workload_name(a), "precision": eng.precision,
                            "parallelism": f"node-range partition x{world}" if world > 1 else "single GPU",
                            "cuda_graph": not a.no_graph, "weights": "seeded default init",
+                           **({"edge_kernel_mode": a.edge_mode} if a.edge_mode else {}),
                            "l2": "inputs larger than L2 (level-1 %s features %.1f GB per buffer)" % (
                                ("angle", a.nodes * a.k * a.k * a.hidden * 4 / 1e9) if a.model == "remus"
                                else ("edge", a.nodes * a.k * a.hidden * 4 / 1e9))},
