@@ -164,15 +164,10 @@ def run_g4c(a):
     if a.edge_mode:
         ops.L.check(ops.L.lib().g4c_debug_set_edge_mode(a.edge_mode))
     g, params = build_workload(a, a.nodes)
-    if world > 1 and a.model == "remus":
-        # edge-halo partition (graphs4cfd_b200/partition_remus.py)
-        from graphs4cfd_b200.partition_remus import PartitionedRemusRollout
-        eng = PartitionedRemusRollout(params, g, rank=rank, world=world, precision=a.precision, device=dev,
-                                      cuda_graph=not a.no_graph)
-    elif world > 1:
-        from graphs4cfd_b200.partition import PartitionedRollout
-        eng = PartitionedRollout(params, g, rank=rank, world=world, precision=a.precision, device=dev,
-                                 cuda_graph=not a.no_graph)
+    if world > 1:
+        # node-range partition; REMuS-GNN gets the edge-halo variant (graphs4cfd_b200/partition_remus.py)
+        from graphs4cfd_b200.partition import partitioned_rollout
+        eng = partitioned_rollout(params, g, rank=rank, world=world, precision=a.precision, device=dev, cuda_graph=not a.no_graph)
     else:
         eng = Rollout(params, g, precision=a.precision, device=dev, cuda_graph=not a.no_graph)
     N_local, nf, fw = eng.N, eng.nf, eng.field_width

@@ -484,3 +484,12 @@ class PartitionedRollout:
         full[self.own.to(self.device)] = local_out
         dist.all_reduce(full)
         return full
+
+
+def partitioned_rollout(params, graph, rank: int, world: int, **kw):
+    """Rank-local rollout engine for either model family: REMuS-GNN state dicts (they hold ``angle_encoder*`` keys,
+    nn/remus_gnn.py:19-57) get the edge-halo partition of partition_remus.py, everything else the node-halo one."""
+    if any(k.startswith("angle_encoder") for k in params):
+        from .partition_remus import PartitionedRemusRollout
+        return PartitionedRemusRollout(params, graph, rank, world, **kw)
+    return PartitionedRollout(params, graph, rank, world, **kw)

@@ -198,3 +198,17 @@ def test_remus_plan_invariants(world):
                 assert (P["dn_src"] < Pl["e_rows"]).all()
                 assert Pl["down_xchg"].n_recv == Pl["n_dghost"] * k
                 assert (Pl["it_x"] < P["n_own"] + P["n_ighost"]).all()       # level l-1 interpolates from level l
+
+
+def test_partitioned_rollout_factory_dispatch(monkeypatch):
+    """partition.partitioned_rollout picks the engine from the state-dict keys and forwards its arguments unchanged."""
+    from graphs4cfd_b200 import partition, partition_remus
+    calls = []
+    monkeypatch.setattr(partition, "PartitionedRollout", lambda *a, **k: calls.append(("mus", a, k)) or "mus")
+    monkeypatch.setattr(partition_remus, "PartitionedRemusRollout", lambda *a, **k: calls.append(("remus", a, k)) or "remus")
+    kw = dict(precision="fp32", device="cuda:1", cuda_graph=True)
+    assert partition.partitioned_rollout({"node_encoder.MLP.linear_1.weight": 0}, "g", rank=1, world=2, **kw) == "mus"
+    assert partition.partitioned_rollout({"angle_encoder2.MLP.linear_1.weight": 0}, "g", rank=1, world=2, **kw) == "remus"
+    assert [c[0] for c in calls] == ["mus", "remus"]
+    for _, a, k in calls:
+        assert a[1:] == ("g", 1, 2) and k == kw
