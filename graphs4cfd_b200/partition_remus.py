@@ -35,7 +35,7 @@ SFX = {1: "", 2: "2", 3: "3"}
 # ------------------------------------------------------------------------------- global structure
 def _level_structure(g, l):
     """(V_l node ids ascending [level-1 numbering], k, source of every edge as an index into V_l)."""
-    ei = _np(getattr(g, "edge_index" + SFX[l])).astype(np.int64)
+    ei = _np(getattr(g, "edge_index" + SFX[l])).astype(np.int64, copy=False)
     E = ei.shape[1]
     k = int((ei[1] == ei[1][0]).sum())
     if E % k or not (ei[1].reshape(-1, k) == ei[1].reshape(-1, k)[:, :1]).all():
@@ -73,8 +73,11 @@ def _halo(world, owner_of, need_lists, local_of_own, recv_off, unit=1):
     return out
 
 
-def build_remus_rank_plans(g, world: int):
-    """Per-rank plans (numpy / CPU tensors) of every rank; identical on every process."""
+def build_remus_rank_plans(g, world: int, only_rank: Optional[int] = None):
+    """Per-rank plans (numpy / CPU tensors); identical on every process.  The exchange lists need every rank's ghost sets,
+    but the heavy per-rank arrays (angle topology and attributes, unit vectors, interpolation lists) are only built for
+    `only_rank` when it is given (at 4M nodes the angle attributes of all ranks together are 2.3 GB per process)."""
+    heavy = lambda r: only_rank is None or r == only_rank
     owner1 = strip_owners(g.pos, world)
     nodes, k_of, src_of, owner = {}, {}, {}, {}
     for l in (1, 2, 3):
@@ -110,7 +113,7 @@ def build_remus_rank_plans(g, world: int):
             dghost[lo].append(d)
 
     for l in (1, 2, 3):
-        a_idx = _np(getattr(g, "angle_index" + SFX[l])).astype(np.int64)
+        a_idx = _np(getattr(g, "angle_index" + SFX[l])).astype(np.int64, copy=False)
         E = nodes[l].size * k
         if a_idx.shape[1] != E * k or not (a_idx[1] == np.repeat(np.arange(E), k)).all():
             raise NotImplementedError("REMuS partition: angles must be stored as k per edge, grouped by edge")
@@ -122,6 +125,8 @@ def build_remus_rank_plans(g, world: int):
             o, gh, dg = own[l][r], ghost[l][r], dghost[l][r]
             P["own"], P["n_own"], P["n_ghost"], P["n_dghost"] = o, o.size, gh.size, dg.size
             P["e_rows"] = (o.size + gh.size + dg.size) * k
+            if not heavy(r):
+                continue
             g2l = own_pos[l][r].copy()
             g2l[gh] = o.size + np.arange(gh.size)
             own_e = _expand(o, k)                          # global ids of my edges, local order
@@ -145,7 +150,7 @@ def build_remus_rank_plans(g, world: int):
     # ---- DownEdgeMP lo -> lo+1
     for lo, name in ((1, "12"), (2, "23")):
         hi = lo + 1
-        a_idx = _np(getattr(g, "angle_index" + name)).astype(np.int64)
+        a_idx = _np(getattr(g, "angle_index" + name)).astype(np.int64, copy=False)
         a_attr = getattr(g, "angle_attr" + name).float()
         E_hi = nodes[hi].size * k
         order = np.argsort(a_idx[1], kind="stable")
@@ -153,6 +158,8 @@ def build_remus_rank_plans(g, world: int):
             raise NotImplementedError("REMuS partition: k inter-level angles per coarse edge")
         by_edge = order.reshape(E_hi, k)                   # angle rows of every coarse edge, caller's order inside
         for r in range(world):
+            if not heavy(r):
+                continue
             P, Pl = plans[r]["levels"][hi], plans[r]["levels"][lo]
             d2l = own_pos[lo][r].copy()
             free = d2l[dghost[lo][r]] < 0                  # a down ghost that is also owned keeps its own row
@@ -171,8 +178,8 @@ def build_remus_rank_plans(g, world: int):
     # ---- UpEdgeMP hi <- lo = hi+1: interpolation sources
     for hi, name in ((2, "32"), (1, "21")):
         lo = hi + 1
-        y_idx = _np(getattr(g, "y_idx_" + name)).astype(np.int64)
-        x_idx = _np(getattr(g, "x_idx_" + name)).astype(np.int64)
+        y_idx = _np(getattr(g, "y_idx_" + name)).astype(np.int64, copy=False)
+        x_idx = _np(getattr(g, "x_idx_" + name)).astype(np.int64, copy=False)
         w = getattr(g, "weights_" + name).float().reshape(-1)
         n_y = nodes[hi].size
         ki = y_idx.size // n_y
@@ -188,6 +195,10 @@ def build_remus_rank_plans(g, world: int):
         for r in range(world):
             P = plans[r]["levels"][hi]
             Plo = plans[r]["levels"][lo]
+            Plo["n_ighost"] = ighost[r].size
+            Plo["interp_xchg"] = xs[r]
+            if not heavy(r):
+                continue
             i2l = own_pos[lo][r].copy()
             i2l[ighost[r]] = Plo["n_own"] + np.arange(ighost[r].size)
             rows = _expand(own[hi][r], ki)
@@ -195,8 +206,6 @@ def build_remus_rank_plans(g, world: int):
             assert (P["it_x"] >= 0).all()
             P["it_w"] = w[torch.from_numpy(rows)].contiguous()
             P["it_k"] = ki
-            Plo["n_ighost"] = ighost[r].size
-            Plo["interp_xchg"] = xs[r]
     for r in range(world):
         plans[r]["own1"] = own[1][r]
     return plans
@@ -382,7 +391,7 @@ class PartitionedRemusRollout:
         if self.precision == "auto":
             self.precision = "fp16x3" if self.H == 128 else "fp32"
         self.packs = {}
-        self.plan = plan = build_remus_rank_plans(graph, world)[rank]
+        self.plan = plan = build_remus_rank_plans(graph, world, only_rank=rank)[rank]
         L, k = plan["levels"], plan["k"]
         field, glob, omega = local_inputs(graph, plan)
         self.node_in = field.to(dev)

@@ -212,3 +212,28 @@ def test_partitioned_rollout_factory_dispatch(monkeypatch):
     assert [c[0] for c in calls] == ["mus", "remus"]
     for _, a, k in calls:
         assert a[1:] == ("g", 1, 2) and k == kw
+
+
+def test_only_rank_plan_equals_full_plan():
+    """only_rank skips the other ranks' heavy arrays but must give this rank exactly the plan of the full build."""
+    from graphs4cfd_b200.partition_remus import build_remus_rank_plans
+    from graphs4cfd_b200.partition import Xchg
+    g, _ = _mesh_and_params(n=1500)
+    world, r = 4, 2
+    full = build_remus_rank_plans(g, world)[r]
+    mine = build_remus_rank_plans(g, world, only_rank=r)[r]
+    assert full["k"] == mine["k"] and np.array_equal(full["own1"], mine["own1"])
+    for l in (1, 2, 3):
+        A, B = full["levels"][l], mine["levels"][l]
+        assert set(A) == set(B), set(A) ^ set(B)
+        for key in A:
+            a, b = A[key], B[key]
+            if isinstance(a, Xchg):
+                assert np.array_equal(a.send_idx, b.send_idx) and a.send_splits == b.send_splits
+                assert a.recv_splits == b.recv_splits and a.recv_off == b.recv_off and a.active == b.active
+            elif isinstance(a, torch.Tensor):
+                assert torch.equal(a, b), key
+            elif isinstance(a, np.ndarray):
+                assert np.array_equal(a, b), key
+            else:
+                assert a == b, key
