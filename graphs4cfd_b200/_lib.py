@@ -112,6 +112,7 @@ EXPORTS = {
     "g4c_debug_tc_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_int32, C.c_void_p, C.c_void_p]),
     "g4c_debug_profile": (C.c_int, [C.c_void_p]),
     "g4c_debug_set_edge_mode": (C.c_int, [C.c_int32]),
+    "g4c_debug_tma": (C.c_int, [C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "g4c_debug_tc2": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
 }
 

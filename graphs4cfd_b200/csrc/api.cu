@@ -219,6 +219,12 @@ int g4c_debug_profile(uint64_t* out64) {
     return edge_pair_profile(reinterpret_cast<unsigned long long*>(out64));
 }
 
+int g4c_debug_tma(int32_t test, const float* src, int64_t rows, int32_t k, const int32_t* idx, float* out, int32_t c0, int32_t j, int32_t n0,
+                  void* stream) {
+    if (test < 0 || test > 3 || !src || !out || rows < 1 || k < 1 || (test == 2 && !idx)) { set_error("g4c_debug_tma: bad arguments"); return G4C_EINVAL; }
+    return tma_test_launch(test, src, rows, k, idx, out, c0, j, n0, static_cast<cudaStream_t>(stream));
+}
+
 int g4c_debug_set_edge_mode(int32_t mode) {
     if (mode < 0 || mode > 3) { set_error("g4c_debug_set_edge_mode: mode=%d (0..3)", mode); return G4C_EINVAL; }
     edge_pair_set_mode(mode);

@@ -680,6 +680,13 @@ static bool encode(CUtensorMap* m, const float* base, int64_t rows, int k, int b
     return r == CUDA_SUCCESS;
 }
 
+// the same, callable from tma_test.cu (swizzle given in bytes: 32 / 64 / 128)
+bool encode_rows(CUtensorMap* m, const float* base, int64_t rows, int k, int box_cols, int swizzle_bytes, int box_rows) {
+    const CUtensorMapSwizzle swz = swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                                                                      : CU_TENSOR_MAP_SWIZZLE_128B;
+    return encode(m, base, rows, k, box_cols, swz, box_rows);
+}
+
 }  // namespace ep4
 
 int edge_pair_tma_profile(unsigned long long* out64) {

@@ -19,6 +19,7 @@ int edge_pair_mode();
 void edge_pair_set_mode(int mode);
 bool edge_pair_tma_supported(const EdgeArgs& a);
 int edge_pair_tma_launch(const EdgeArgs& a, int mode, cudaStream_t st);
-int edge_pair_tma_profile(unsigned long long* out64);         // phase profile of the TMA variants (needs -DG4C_PROFILE)
+int edge_pair_tma_profile(unsigned long long* out64);
+int tma_test_launch(int test, const float* src, int64_t rows, int k, const int32_t* idx, float* out, int c0, int j, int n0, cudaStream_t st);   // tma_test.cu         // phase profile of the TMA variants (needs -DG4C_PROFILE)
 
 }  // namespace g4c

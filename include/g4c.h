@@ -304,6 +304,12 @@ G4C_API int g4c_debug_profile(uint64_t* out64);
  * G4C_EDGE_MODE sets the initial value. */
 G4C_API int g4c_debug_set_edge_mode(int32_t mode);
 
+/* EXPERIMENTAL: one-warp hardware self tests of the bulk-tensor (TMA) copies the variants above rely on (csrc/tma_test.cu):
+ * 0 = 3-D tile load, 1 = 3-D tile store, 2 = gather4 load, 3 = tile load hanging over the end of the tensor.
+ * src = [rows * k, 128] fp32 (test 2: [rows, 128]); out = [32, 16] (test 1: [rows * k, 128]); tile origin (c0, j, n0). */
+G4C_API int g4c_debug_tma(int32_t test, const float* src, int64_t rows, int32_t k, const int32_t* idx, float* out,
+                          int32_t c0, int32_t j, int32_t n0, void* stream);
+
 G4C_API int g4c_host_guillard(const int64_t* senders, int64_t n, int32_t k, uint8_t* coarse_mask);
 
 #ifdef __cplusplus
