@@ -3,7 +3,7 @@
 // makes the per-node products P_r, P_c of the split edge model (g4c_rowmlp_tc_fwd).
 //
 // Same machinery as mp_edge_pair.cu — weights resident in shared memory as half images per CTA, A operands and
-// accumulators in TMEM, loader warps + tcgen05.cp as the row -> lane transposer, two chains alternating so the
+// accumulators in TMEM, loader warps (cp.async rings, lane = row read-back, tcgen05.st), two chains alternating so the
 // MMAs of one tile overlap the epilogue of the other — with these differences:
 //   * a "slot" is a pair-tile (256 consecutive rows, 128 per CTA); the tiles a pair owns alternate chains;
 //   * layer 1 consumes the concatenated input K-block by K-block (64 columns each, or one K = 16 step for a
