@@ -152,6 +152,8 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, int c0, int c
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // every bulk group this thread committed has finished READING its shared-memory source
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... all but the most recent one
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
 // kLoad: 0 = every row piece by cp.async (mode 1), 1 = e / P_c tiles by TMA (mode 2), 2 = P_r[src] by TMA gather4 as well (mode 3)
 template <int kLoad>
@@ -218,7 +220,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_tma_kern
         // (tile base = ost0 & ~1023, the other chunk = ost0 ^ 16: one live register)
         const uint32_t ost0 = sb + (uint32_t)offsetof(Smem, ostage) + (uint32_t)(etid >> 5) * OPIECE + (uint32_t)lane * 32u +
                               ((uint32_t)((lane >> 2) & 1) << 4);
-        // lane 0 issues, commits and waits for every bulk store of this warp (bulk groups are per thread)
+        // lane 0 issues, commits and waits for every bulk store of this warp (bulk groups are per thread).
+        // Two-layer MLPs (REMuS angle / edge models) leave the third layer's 32 KiB of weight space unused: there the staging is
+        // double buffered (pieces alternate between two 1 KiB tiles per warp, the wait lets one store stay in flight).
+        const bool two_buf = nl == 2;
+        const uint32_t ost_alt = sb + (uint32_t)offsetof(Smem, w) + 2u * 4u * HIMG + (uint32_t)(etid >> 5) * (2u * OPIECE) +
+                                 (uint32_t)lane * 32u + ((uint32_t)((lane >> 2) & 1) << 4);
         uint32_t n_dfull[2] = {0, 0};
         const bool has_ln = a.gamma != nullptr;
         int pbuf = 0;
@@ -347,15 +354,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_tma_kern
                                     }
                                     // the staging tile is free once the previous piece's bulk store has read it; everything above
                                     // (normalise, aggregate, SELU of this piece) ran while the TMA engine was reading
-                                    if (lane == 0) bulk_wait_read0();
+                                    const uint32_t ost = two_buf ? ost_alt + (uint32_t)((i8 >> 3) & 1) * OPIECE : ost0;
+                                    if (lane == 0) {
+                                        if (two_buf) bulk_wait_read1(); else bulk_wait_read0();
+                                    }
                                     __syncwarp();
-                                    sts_f4(ost0, o[0], o[1], o[2], o[3]);
-                                    sts_f4(ost0 ^ 16u, o[4], o[5], o[6], o[7]);
+                                    sts_f4(ost, o[0], o[1], o[2], o[3]);
+                                    sts_f4(ost ^ 16u, o[4], o[5], o[6], o[7]);
                                     fence_proxy_async();        // generic-proxy writes -> visible to the TMA engine
                                     __syncwarp();
                                     // rows past the last target hold values of no edge; the tensor map's bounds clip them
                                     if (lane == 0) {
-                                        tma_store_3d(&tm.e_out, cq * 32 + i8, j, n_unit0 + lq * 32, ost0 & ~1023u);
+                                        tma_store_3d(&tm.e_out, cq * 32 + i8, j, n_unit0 + lq * 32, ost & ~1023u);
                                         bulk_commit();
                                     }
                                 }

@@ -87,3 +87,9 @@ def test_stage_and_staging_offsets_keep_the_swizzle_phase():
     assert ostage == 192 * 1024
     for w in range(16):
         assert (ostage + w * 1024) % 256 == 0 and (ostage + w * 1024) % 1024 == 0      # "& ~1023" recovers the tile base
+    # two-layer MLPs double-buffer the staging in the unused third-layer weight space: w[2] = 2 * 4 * HIMG bytes into the struct
+    w2 = 2 * 4 * 64 * 128
+    for w in range(16):
+        for buf in range(2):
+            assert (w2 + w * 2048 + buf * 1024) % 1024 == 0
+    assert w2 + 16 * 2048 == 3 * 4 * 64 * 128        # exactly fills w[2]
