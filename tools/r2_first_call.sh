@@ -17,4 +17,8 @@ for m in 1 2 3; do
   timeout 120 python tools/bench_edge.py --modes 0,$m 2>&1 | tail -4 > gpurun_out/r2_bench_edge_mode${m}.log
   timeout 120 python tools/bench_edge.py --modes 0,$m --layers 2 --k 6 2>&1 | tail -4 >> gpurun_out/r2_bench_edge_mode${m}.log
 done
+# memcheck of the small cases of every mode (shared-memory / global out-of-bounds, misaligned bulk copies)
+G4C_TEST_EXPERIMENTAL=1 timeout 600 compute-sanitizer --tool memcheck --print-limit 20 python -m pytest tests/test_gpu_edge_pair.py -m gpu -q \
+  -k "tma_modes and 77-6" > gpurun_out/r2_memcheck.full 2>&1
+tail -25 gpurun_out/r2_memcheck.full > gpurun_out/r2_memcheck.log
 tail -n 20 gpurun_out/r2_*.log
