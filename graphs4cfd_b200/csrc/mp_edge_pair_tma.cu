@@ -5,8 +5,9 @@
 //
 // Why (profiles/r1d_edge_pair_v3_phases.txt): v3 is limited by the SM's load/store pipe, not by HBM
 // or the tensor pipe.  Per 128-edge slot the pipe handles 384 LDGSTS (8 row pieces each), 384 lane = row LDS.128 and
-// 128 STG.256 that each touch 32 different 128-byte lines (one line per pass), about 10k cycles against the 6.7k-cycle
-// HBM bound.  This version takes the two regular streams off that pipe:
+// 64 STG.256 that each touch 32 different 128-byte lines (one line per pass), about 7.5k cycles against the 6.7k-cycle
+// HBM bound (tools/edge_kernel_model.py), and the epilogue's stores queue behind the loaders' copies.  This version takes
+// the regular streams off that pipe:
 //   mode 1  e' leaves through shared memory and the TMA engine: each epilogue warp stages 32 rows x 8 columns (1 KiB,
 //           SWIZZLE_32B so that lane = row STS.128 are bank-conflict free) and one elected lane issues
 //           cp.async.bulk.tensor.3d.global.shared::cta (box 8 x 1 x 32 of the [N, k, 128] view of e').  The 24 KiB
