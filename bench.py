@@ -38,7 +38,7 @@ def parse():
                     help="mus: the MuS-GNN workload of BASELINE.json's metric (default); remus: the 3-scale REMuS-GNN of "
                          "configs[2] (a measurement case, not the driver's bench line; N > 1 uses the edge-halo partition)")
     ap.add_argument("--edge-mode", type=int, default=int(os.environ.get("G4C_EDGE_MODE", "0")),
-                    help="0 (default): the measured edge kernel; 1..3: experimental TMA variants (csrc/mp_edge_pair_tma.cu)")
+                    help="0 (default): the measured edge kernel; 1..4: experimental TMA variants (csrc/mp_edge_pair_tma.cu)")
     ap.add_argument("--precision", default=os.environ.get("G4C_PRECISION", "auto"),
                     help="auto (fp16x3 tensor-core path when hidden=128, else fp32) | fp16x3 | fp32")
     ap.add_argument("--no-graph", action="store_true")

@@ -226,7 +226,7 @@ int g4c_debug_tma(int32_t test, const float* src, int64_t rows, int32_t k, const
 }
 
 int g4c_debug_set_edge_mode(int32_t mode) {
-    if (mode < 0 || mode > 3) { set_error("g4c_debug_set_edge_mode: mode=%d (0..3)", mode); return G4C_EINVAL; }
+    if (mode < 0 || mode > 4) { set_error("g4c_debug_set_edge_mode: mode=%d (0..4)", mode); return G4C_EINVAL; }
     edge_pair_set_mode(mode);
     return G4C_OK;
 }

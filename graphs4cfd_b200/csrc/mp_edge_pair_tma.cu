@@ -1,6 +1,6 @@
 // mp_edge_pair_tma.cu — edge_pair_kernel (mp_edge_pair.cu, "v3") with bulk-tensor (TMA) data paths.  "v4".
 //
-// STATUS: EXPERIMENTAL and OPT-IN (G4C_EDGE_MODE=1|2|3 or g4c_debug_set_edge_mode): written after the round's GPU budget
+// STATUS: EXPERIMENTAL and OPT-IN (G4C_EDGE_MODE=1..4 or g4c_debug_set_edge_mode): written after the round's GPU budget
 // was spent; it compiles for sm_100a but has NOT run on hardware yet.  The default path is the v3 kernel, untouched.
 //
 // Why (profiles/r1d_edge_pair_v3_phases.txt): v3 is limited by the SM's load/store pipe, not by HBM
@@ -19,6 +19,8 @@
 //           none of the e / P_c address arithmetic).
 //   mode 3  additionally the gathered P_r[src] pieces arrive through TMA (tile::gather4: four source rows per copy, eight
 //           copies per stage issued by lanes 0-7 with their own row coordinates): no LDGSTS at all in the loaders.
+//   mode 4  mode 3 with 96 / 48 registers per epilogue / loader thread instead of 88 / 64 (the loaders of mode 3 hold no
+//           address arrays any more).
 // Restrictions (checked by the launcher, which falls back to v3): fixed in-degree (fixed_k > 0), edges stored in
 // aggregation order (no edge_perm / tgt_perm).  That covers the level-1 kNN launches and every REMuS angle level,
 // i.e. the launches that dominate the step.  Arithmetic, TMEM layout, MMA issue, hidden epilogues and the LayerNorm
@@ -41,8 +43,7 @@ constexpr int NT = 896;                  // warps 0-15 epilogue, 16-23 loaders, 
 constexpr int N_EPI_WARPS = 16;
 constexpr int N_LOAD_WARPS = 8;
 constexpr int W_LOAD0 = 16, W_MMA = 24;
-constexpr int kRegsEpi = 88, kRegsLoad = 64, kRegsMisc = 24;
-static_assert(512 * kRegsEpi + 256 * kRegsLoad + 128 * kRegsMisc <= 896 * 72, "register budget");
+constexpr int kRegsMisc = 24;       // epilogue / loader registers are template parameters of the kernel (88 / 64 as in v3, or 96 / 48)
 
 constexpr int SCOLS = 16;                // columns per loader stage
 constexpr int NCS = H / SCOLS;
@@ -157,9 +158,10 @@ __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.
 __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
 // kLoad: 0 = every row piece by cp.async (mode 1), 1 = e / P_c tiles by TMA (mode 2), 2 = P_r[src] by TMA gather4 as well (mode 3)
-template <int kLoad>
+template <int kLoad, int kRegsEpi = 88, int kRegsLoad = 64>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_tma_kernel(const EdgeArgs a, const __grid_constant__ Maps tm) {
     constexpr bool kTmaLoad = kLoad >= 1, kGather = kLoad == 2;
+    static_assert(512 * kRegsEpi + 256 * kRegsLoad + 128 * kRegsMisc <= 896 * 72, "register budget");
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     Smem& s = *reinterpret_cast<Smem*>(smem_raw);
     if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
@@ -721,7 +723,7 @@ int edge_pair_mode() {
     if (g_edge_mode < 0) {
         const char* e = std::getenv("G4C_EDGE_MODE");
         g_edge_mode = e ? std::atoi(e) : 0;
-        if (g_edge_mode < 0 || g_edge_mode > 3) g_edge_mode = 0;
+        if (g_edge_mode < 0 || g_edge_mode > 4) g_edge_mode = 0;
     }
     return g_edge_mode;
 }
@@ -746,7 +748,8 @@ int edge_pair_tma_launch(const EdgeArgs& a, int mode, cudaStream_t st) {
     if (!configured) {
         if (cudaFuncSetAttribute(ep4::edge_tma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
             cudaFuncSetAttribute(ep4::edge_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
-            cudaFuncSetAttribute(ep4::edge_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+            cudaFuncSetAttribute(ep4::edge_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+            cudaFuncSetAttribute(ep4::edge_tma_kernel<2, 96, 48>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
             return check_launch("edge_tma_kernel attribute");
         configured = true;
     }
@@ -759,7 +762,8 @@ int edge_pair_tma_launch(const EdgeArgs& a, int mode, cudaStream_t st) {
     }
     const int64_t n_units = (a.n_targets + 127) / 128, n_up = (n_units + 1) / 2;
     const int pairs = (int)std::min<int64_t>(n_up, n_sm / 2);
-    if (mode >= 3) ep4::edge_tma_kernel<2><<<2 * pairs, ep4::NT, smem, st>>>(a, tm);
+    if (mode >= 4) ep4::edge_tma_kernel<2, 96, 48><<<2 * pairs, ep4::NT, smem, st>>>(a, tm);
+    else if (mode == 3) ep4::edge_tma_kernel<2><<<2 * pairs, ep4::NT, smem, st>>>(a, tm);
     else if (mode == 2) ep4::edge_tma_kernel<1><<<2 * pairs, ep4::NT, smem, st>>>(a, tm);
     else ep4::edge_tma_kernel<0><<<2 * pairs, ep4::NT, smem, st>>>(a, tm);
     count_launch();

@@ -14,7 +14,7 @@ int edge_pair_profile(unsigned long long* out64);            // phase profile (n
 int row_pair_launch(const G4cRowTcDesc& d, cudaStream_t st);   // mp_row_pair.cu
 
 // mp_edge_pair_tma.cu: experimental bulk-tensor (TMA) variants of the edge kernel, selected by G4C_EDGE_MODE / g4c_debug_set_edge_mode
-// (0 = the v3 kernel, default; 1 = e' through shared memory + TMA stores; 2 = 1 + e / P_c tiles through TMA loads; 3 = 2 + P_r[src] through TMA gather4)
+// (0 = the v3 kernel, default; 1 = e' through shared memory + TMA stores; 2 = 1 + e / P_c tiles through TMA loads; 3 = 2 + P_r[src] through TMA gather4; 4 = 3 with 96 / 48 registers per epilogue / loader thread)
 int edge_pair_mode();
 void edge_pair_set_mode(int mode);
 bool edge_pair_tma_supported(const EdgeArgs& a);

@@ -300,7 +300,7 @@ G4C_API int g4c_debug_profile(uint64_t* out64);
 
 /* EXPERIMENTAL: variant of the kernel behind g4c_edge_aggr_fwd for launches with fixed_k > 0 and no permutations
  * (csrc/mp_edge_pair_tma.cu).  0 = default kernel; 1 = e' staged in shared memory and written by TMA tensor stores;
- * 2 = 1 + e / P_c tiles read by TMA tensor loads; 3 = 2 + the gathered P_r rows read by TMA gather4.  Same result as mode 0.  The environment variable
+ * 2 = 1 + e / P_c tiles read by TMA tensor loads; 3 = 2 + the gathered P_r rows read by TMA gather4; 4 = 3 with another register split.  Same result as mode 0.  The environment variable
  * G4C_EDGE_MODE sets the initial value. */
 G4C_API int g4c_debug_set_edge_mode(int32_t mode);
 

@@ -107,12 +107,12 @@ def _set_mode(mode):
 
 @gpu
 @experimental
-@pytest.mark.parametrize("mode", [1, 2, 3], ids=["mode1", "mode2", "mode3"])
+@pytest.mark.parametrize("mode", [1, 2, 3, 4], ids=["mode1", "mode2", "mode3", "mode4"])
 @pytest.mark.parametrize("n,k", [(1000, 6), (256, 5), (77, 6), (40000, 6), (128, 1), (129, 2)])
 @pytest.mark.parametrize("n_layers", [3, 2])
 @pytest.mark.parametrize("want_e", [True, False])
 def test_edge_pair_tma_modes_match_default(mode, n, k, n_layers, want_e):
-    """Modes 1 / 2 / 3 move the same values through different data paths: results must equal mode 0 bit for bit, and the fp64
+    """Modes 1 .. 4 move the same values through different data paths: results must equal mode 0 bit for bit, and the fp64
     restatement within the kernel's tolerance."""
     dev = torch.device("cuda")
     g = torch.Generator().manual_seed(n + k)

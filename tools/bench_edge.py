@@ -17,7 +17,7 @@ ap.add_argument("--spread", type=int, default=2000, help="sources are drawn with
 ap.add_argument("--layers", type=int, default=3)
 ap.add_argument("--no-e", action="store_true")
 ap.add_argument("--act", default="selu")
-ap.add_argument("--modes", default="0", help="comma-separated kernel variants to time (0 = default, 1 / 2 / 3 = experimental TMA data paths, "
+ap.add_argument("--modes", default="0", help="comma-separated kernel variants to time (0 = default, 1 .. 4 = experimental TMA data paths, "
                                             "csrc/mp_edge_pair_tma.cu); the outputs of every variant are compared with the first one's")
 a = ap.parse_args()
 
