@@ -37,8 +37,8 @@ def parse():
     ap.add_argument("--model", default="mus", choices=["mus", "remus"],
                     help="mus: the MuS-GNN workload of BASELINE.json's metric (default); remus: the 3-scale REMuS-GNN of "
                          "configs[2] (a measurement case, not the driver's bench line; N > 1 uses the edge-halo partition)")
-    ap.add_argument("--edge-mode", type=int, default=int(os.environ.get("G4C_EDGE_MODE", "0")),
-                    help="0 (default): the measured edge kernel; 1..4: experimental TMA variants (csrc/mp_edge_pair_tma.cu)")
+    ap.add_argument("--edge-variant", default="auto", choices=["auto", "v3", "v5"],
+                    help="kernel behind g4c_edge_aggr_fwd: auto (default: v5 on fixed in-degree launches, v3 otherwise) or pinned")
     ap.add_argument("--precision", default=os.environ.get("G4C_PRECISION", "auto"),
                     help="auto (fp16x3 tensor-core path when hidden=128, else fp32) | fp16x3 | fp32")
     ap.add_argument("--no-graph", action="store_true")
@@ -161,8 +161,7 @@ def run_g4c(a):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    if a.edge_mode:
-        ops.L.check(ops.L.lib().g4c_debug_set_edge_mode(a.edge_mode))
+    ops.EDGE_VARIANT_DEFAULT = a.edge_variant
     g, params = build_workload(a, a.nodes)
     if world > 1:
         # node-range partition; REMuS-GNN gets the edge-halo variant (graphs4cfd_b200/partition_remus.py)
@@ -252,7 +251,7 @@ def run_g4c(a):
                 "config": {"workload": workload_name(a), "precision": eng.precision,
                            "parallelism": f"node-range partition x{world}" if world > 1 else "single GPU",
                            "cuda_graph": not a.no_graph, "weights": "seeded default init",
-                           **({"edge_kernel_mode": a.edge_mode} if a.edge_mode else {}),
+                           **({"edge_kernel": a.edge_variant} if a.edge_variant != "auto" else {}),
                            "l2": "inputs larger than L2 (level-1 %s features %.1f GB per buffer)" % (
                                ("angle", a.nodes * a.k * a.k * a.hidden * 4 / 1e9) if a.model == "remus"
                                else ("edge", a.nodes * a.k * a.hidden * 4 / 1e9))},

@@ -12,8 +12,9 @@ LIB_PATH = os.environ.get("G4C_LIB", os.path.join(_HERE, "libg4c.so"))      # G4
 
 ACT_NONE, ACT_SELU, ACT_TANH = 0, 1, 2
 AGGR_MEAN, AGGR_SUM = 0, 1
-PREC_FP32, PREC_FP16X3, PREC_BF16 = 0, 1, 2
-PRECISIONS = {"fp32": PREC_FP32, "fp16x3": PREC_FP16X3, "bf16": PREC_BF16}
+PREC_FP32, PREC_FP16X3 = 0, 1
+PRECISIONS = {"fp32": PREC_FP32, "fp16x3": PREC_FP16X3}
+EDGE_AUTO, EDGE_V3, EDGE_V5 = 0, 1, 2
 ACTS = {None: ACT_NONE, "none": ACT_NONE, "selu": ACT_SELU, "tanh": ACT_TANH}
 MAX_LAYERS, MAX_SEGS = 3, 3
 
@@ -23,8 +24,7 @@ _i32p = C.c_void_p
 
 class Mlp(C.Structure):
     _fields_ = [("n_layers", C.c_int32), ("in_width", C.c_int32), ("hidden", C.c_int32), ("out_width", C.c_int32),
-                ("W_t", _f32p * MAX_LAYERS), ("b", _f32p * MAX_LAYERS), ("ln_gamma", _f32p), ("ln_beta", _f32p),
-                ("W_pack", C.c_void_p * MAX_LAYERS), ("w_inv_scale", C.c_float * MAX_LAYERS), ("_pad", C.c_int32)]
+                ("W_t", _f32p * MAX_LAYERS), ("b", _f32p * MAX_LAYERS), ("ln_gamma", _f32p), ("ln_beta", _f32p)]
 
 
 class Seg(C.Structure):
@@ -51,7 +51,7 @@ class EdgeDesc(C.Structure):
                 ("act_e_out", C.c_int32), ("aggr", C.c_int32), ("rowptr", _i32p), ("src", _i32p), ("edge_perm", _i32p),
                 ("tgt_perm", _i32p), ("e_in", _f32p), ("P_r", _f32p), ("P_c", _f32p), ("e_out", _f32p),
                 ("agg_out", _f32p), ("W", C.c_void_p * 3), ("inv_scale", C.c_float * 3), ("p_scale", C.c_float),
-                ("bias", _f32p * 3), ("gamma", _f32p), ("beta", _f32p)]
+                ("bias", _f32p * 3), ("gamma", _f32p), ("beta", _f32p), ("variant", C.c_int32), ("_pad", C.c_int32)]
 
 
 class RowTcDesc(C.Structure):
@@ -109,10 +109,8 @@ EXPORTS = {
     "g4c_halo_pack": (C.c_int, [C.POINTER(HaloDesc), C.c_void_p]),
     "g4c_halo_unpack": (C.c_int, [C.POINTER(HaloDesc), C.c_void_p]),
     "g4c_host_guillard": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
-    "g4c_debug_tc_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_int32, C.c_void_p, C.c_void_p]),
-    "g4c_debug_profile": (C.c_int, [C.c_void_p]),
-    "g4c_debug_set_edge_mode": (C.c_int, [C.c_int32]),
-    "g4c_debug_tma": (C.c_int, [C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "g4c_debug_profile": (C.c_int, [C.c_int32, C.c_void_p]),
+    "g4c_debug_tma": (C.c_int, [C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "g4c_debug_tc2": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
 }
 

@@ -30,7 +30,6 @@ int check_launch(const char* what) {
 }
 
 int mp_fp32_dispatch(const G4cMpDesc& d, cudaStream_t st);
-int mp_tc_dispatch(const G4cMpDesc& d, cudaStream_t st);
 int rowmlp_fp32_dispatch(const G4cRowMlpDesc& d, cudaStream_t st);
 int seg_reduce_launch(const G4cSegReduceDesc& d, cudaStream_t st);
 int project_launch(const G4cProjectDesc& d, cudaStream_t st);
@@ -38,7 +37,6 @@ int edge_to_node_launch(const G4cEdgeToNodeDesc& d, cudaStream_t st);
 int interp_launch(const G4cInterpDesc& d, cudaStream_t st);
 int step_update_launch(const G4cStepUpdateDesc& d, cudaStream_t st);
 int halo_launch(const G4cHaloDesc& d, cudaStream_t st, bool pack);
-int tc_gemm_test_launch(const float* A, const void* W_pack, float inv_scale, int K, float* D, cudaStream_t st);
 int tc2_test_launch(int test, const float* A, const void* Wpack, float inv_scale, const float* P, float* D, int flags, cudaStream_t st);
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -111,8 +109,10 @@ int g4c_mp_fwd(const G4cMpDesc* d, void* stream) {
     if (d->aggr != G4C_AGGR_MEAN && d->aggr != G4C_AGGR_SUM) { set_error("g4c_mp_fwd: aggr=%d", d->aggr); return G4C_EINVAL; }
     if (d->n_targets == 0) return G4C_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (d->precision == G4C_PREC_FP32) return mp_fp32_dispatch(*d, st);
-    return mp_tc_dispatch(*d, st);
+    if (d->precision != G4C_PREC_FP32) {
+        // the tensor-core block is three calls: g4c_rowmlp_tc_fwd (dual: P_r, P_c), g4c_edge_aggr_fwd, g4c_rowmlp_tc_fwd (node model)
+        set_error("g4c_mp_fwd: precision=%d; this entry point is the fused CUDA-core block (G4C_PREC_FP32)", d->precision); return G4C_EUNSUPPORTED; }
+    return mp_fp32_dispatch(*d, st);
 }
 
 int g4c_rowmlp_tc_fwd(const G4cRowTcDesc* d, void* stream) {
@@ -202,33 +202,21 @@ int g4c_halo_unpack(const G4cHaloDesc* d, void* stream) {
     return halo_launch(*d, static_cast<cudaStream_t>(stream), false);
 }
 
-int g4c_debug_tc_gemm(const float* A, const void* W_pack, float w_inv_scale, int32_t K, float* D, void* stream) {
-    if (!A || !W_pack || !D) { set_error("g4c_debug_tc_gemm: NULL pointer"); return G4C_EINVAL; }
-    return tc_gemm_test_launch(A, W_pack, w_inv_scale, K, D, static_cast<cudaStream_t>(stream));
-}
-
 int g4c_debug_tc2(int32_t test, const float* A, const void* W_pack, float w_inv_scale, const float* P, float* D, int32_t flags, void* stream) {
     if (!A || !W_pack || !D || (test == 2 && !P)) { set_error("g4c_debug_tc2: NULL pointer"); return G4C_EINVAL; }
     return tc2_test_launch(test, A, W_pack, w_inv_scale, P, D, flags, static_cast<cudaStream_t>(stream));
 }
 
-int g4c_debug_profile(uint64_t* out64) {
+int g4c_debug_profile(int32_t variant, uint64_t* out64) {
     if (!out64) { set_error("g4c_debug_profile: NULL pointer"); return G4C_EINVAL; }
     cudaDeviceSynchronize();
-    if (edge_pair_mode() > 0) return edge_pair_tma_profile(reinterpret_cast<unsigned long long*>(out64));
-    return edge_pair_profile(reinterpret_cast<unsigned long long*>(out64));
+    return variant == G4C_EDGE_V3 ? edge_pair_profile(reinterpret_cast<unsigned long long*>(out64))
+                                  : edge_v5_profile(reinterpret_cast<unsigned long long*>(out64));
 }
 
-int g4c_debug_tma(int32_t test, const float* src, int64_t rows, int32_t k, const int32_t* idx, float* out, int32_t c0, int32_t j, int32_t n0,
-                  void* stream) {
-    if (test < 0 || test > 3 || !src || !out || rows < 1 || k < 1 || (test == 2 && !idx)) { set_error("g4c_debug_tma: bad arguments"); return G4C_EINVAL; }
-    return tma_test_launch(test, src, rows, k, idx, out, c0, j, n0, static_cast<cudaStream_t>(stream));
-}
-
-int g4c_debug_set_edge_mode(int32_t mode) {
-    if (mode < 0 || mode > 4) { set_error("g4c_debug_set_edge_mode: mode=%d (0..4)", mode); return G4C_EINVAL; }
-    edge_pair_set_mode(mode);
-    return G4C_OK;
+int g4c_debug_tma(int32_t test, const float* src, int64_t rows, int32_t k, float* out, int32_t c0, int32_t j, int32_t n0, void* stream) {
+    if ((test != 0 && test != 1 && test != 3) || !src || !out || rows < 1 || k < 1) { set_error("g4c_debug_tma: bad arguments"); return G4C_EINVAL; }
+    return tma_test_launch(test, src, rows, k, out, c0, j, n0, static_cast<cudaStream_t>(stream));
 }
 
 int g4c_host_guillard(const int64_t* senders, int64_t n, int32_t k, uint8_t* coarse_mask) {

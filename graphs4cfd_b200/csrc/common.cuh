@@ -58,4 +58,34 @@ void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 int check_launch(const char* what);
 
+// ---- per-DEVICE launch configuration.  cudaFuncSetAttribute and the SM count belong to the current device, and a process may
+// drive several (a model on cuda:1 while cuda:0 is current elsewhere): remember what was configured per device ordinal.
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+}
+inline int device_sms() {
+    static int n_sm[kMaxDevices] = {0};
+    const int dev = current_device();
+    if (n_sm[dev] == 0) {
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        n_sm[dev] = n > 0 ? n : 148;
+    }
+    return n_sm[dev];
+}
+// opt in to `smem` bytes of dynamic shared memory for `kernel` on the current device (once per device and size); `state` is the
+// caller's static per-kernel table.  Returns false when the runtime refuses.
+template <typename K>
+inline bool ensure_dynamic_smem(K kernel, int smem, int (&state)[kMaxDevices]) {
+    const int dev = current_device();
+    if (smem > state[dev]) {
+        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return false;
+        state[dev] = smem;
+    }
+    return true;
+}
+
 }  // namespace g4c

@@ -624,27 +624,18 @@ int edge_pair_profile(unsigned long long* out64) {
 }
 
 int edge_pair_launch(const EdgeArgs& a, cudaStream_t st) {
-    const int mode = edge_pair_mode();          // 0 unless G4C_EDGE_MODE / g4c_debug_set_edge_mode asks for an experimental variant
-    if (mode > 0 && edge_pair_tma_supported(a)) return edge_pair_tma_launch(a, mode, st);
+    // variant: 0 = pick (v5 for fixed in-degree launches without permutations, this kernel otherwise), 1 = this kernel, 2 = v5
+    if (a.variant == G4C_EDGE_V5 || (a.variant == G4C_EDGE_AUTO && edge_v5_supported(a))) return edge_v5_launch(a, st);
+    if (a.variant != G4C_EDGE_AUTO && a.variant != G4C_EDGE_V3) { set_error("g4c_edge_aggr_fwd: variant=%d (0..2)", a.variant); return G4C_EINVAL; }
     if (a.act_e_out != G4C_ACT_NONE && a.act_e_out != G4C_ACT_SELU) {
         // the models only ever apply F.selu to a block's edge / angle output (nn/mus_gnn.py:321, nn/remus_gnn.py:143)
         set_error("g4c_edge_aggr_fwd: act_e_out must be none or selu");
         return G4C_EUNSUPPORTED;
     }
-    static bool configured = false;
+    static int configured[kMaxDevices] = {0};
     const int smem = (int)sizeof(ep::Smem);
-    if (!configured) {
-        if (cudaFuncSetAttribute(ep::edge_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
-            return check_launch("edge_pair_kernel attribute");
-        configured = true;
-    }
-    static int n_sm = 0;
-    if (n_sm == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        if (n_sm <= 0) n_sm = 148;
-    }
+    if (!ensure_dynamic_smem(ep::edge_pair_kernel, smem, configured)) return check_launch("edge_pair_kernel attribute");
+    const int n_sm = device_sms();
     const int64_t n_units = (a.n_targets + 127) / 128, n_up = (n_units + 1) / 2;
     const int pairs = (int)std::min<int64_t>(n_up, n_sm / 2);
     ep::edge_pair_kernel<<<2 * pairs, ep::NT, smem, st>>>(a);

@@ -1,41 +1,43 @@
-// mp_edge_pair_tma.cu — edge_pair_kernel (mp_edge_pair.cu, "v3") with bulk-tensor (TMA) data paths.  "v4".
+// mp_edge_v5.cu — fused edge-MLP + LayerNorm + aggregation kernel for launches with a fixed in-degree (kNN levels and
+// every REMuS angle level: the launches that dominate a rollout step).  Fifth generation of the kernel behind
+// g4c_edge_aggr_fwd; launches with a CSR or a permutation keep the cp.async kernel of mp_edge_pair.cu ("v3").
 //
-// STATUS: EXPERIMENTAL and OPT-IN (G4C_EDGE_MODE=1..4 or g4c_debug_set_edge_mode): written after the round's GPU budget
-// was spent; it compiles for sm_100a but has NOT run on hardware yet.  The default path is the v3 kernel, untouched.
+// Reference arithmetic (graphs4cfd/nn/blocks.py:181-183, 328-330, 376-378):
+//     e' = LN(MLP(cat(e, S[src], T[tgt]))) ;  agg[t] = mean/sum over the in-edges of t of e'
+// with the first Linear split exactly, W1 [e, S[src], T[tgt]] + b1 = W1e e + P_r[src] + P_c[tgt] (see mp_edge_pair.cu).
 //
-// Why (profiles/r1d_edge_pair_v3_phases.txt): v3 is limited by the SM's load/store pipe, not by HBM
-// or the tensor pipe.  Per 128-edge slot the pipe handles 384 LDGSTS (8 row pieces each), 384 lane = row LDS.128 and
-// 64 STG.256 that each touch 32 different 128-byte lines (one line per pass), about 7.5k cycles against the 6.7k-cycle
-// HBM bound (tools/edge_kernel_model.py), and the epilogue's stores queue behind the loaders' copies.  This version takes
-// the regular streams off that pipe:
-//   mode 1  e' leaves through shared memory and the TMA engine: each epilogue warp stages 32 rows x 8 columns (1 KiB,
-//           SWIZZLE_32B so that lane = row STS.128 are bank-conflict free) and one elected lane issues
-//           cp.async.bulk.tensor.3d.global.shared::cta (box 8 x 1 x 32 of the [N, k, 128] view of e').  The 24 KiB
-//           this needs come from storing the loaders' row pieces unpadded with a manual XOR swizzle (64-byte pitch,
-//           16-byte chunk c of row r at c ^ ((r >> 1) & 3) — the SWIZZLE_64B pattern) instead of an 80-byte pitch.
-//   mode 2  additionally the e and P_c[tgt] row pieces of a loader stage arrive as two TMA tiles (box 16 x 1 x 32 of
-//           the [N, k, 128] view of e; box 16 x 32 of P_c; SWIZZLE_64B = the ring's layout) signalled on a per-warp,
-//           per-stage mbarrier; only the gathered P_r[src] pieces stay on cp.async (4 of the 12 LDGSTS per stage, and
-//           none of the e / P_c address arithmetic).
-//   mode 3  additionally the gathered P_r[src] pieces arrive through TMA (tile::gather4: four source rows per copy, eight
-//           copies per stage issued by lanes 0-7 with their own row coordinates): no LDGSTS at all in the loaders.
-//   mode 4  mode 3 with 96 / 48 registers per epilogue / loader thread instead of 88 / 64 (the loaders of mode 3 hold no
-//           address arrays any more).
-// Restrictions (checked by the launcher, which falls back to v3): fixed in-degree (fixed_k > 0), edges stored in
-// aggregation order (no edge_perm / tgt_perm).  That covers the level-1 kNN launches and every REMuS angle level,
-// i.e. the launches that dominate the step.  Arithmetic, TMEM layout, MMA issue, hidden epilogues and the LayerNorm
-// are those of v3; results are expected to be bitwise identical to v3.
+// Work decomposition, TMEM layout, MMA issue and mbarrier protocol are v3's: a CTA pair (cta_group::2, M = 256) owns two
+// consecutive units of 128 targets; slot j of a unit = the j-th in-edge of each of its targets, so tile row m always
+// belongs to target m; two chains (even / odd slots) alternate in TMEM: columns [256c, +128) accumulator, [+128, +64) A
+// hi, [+192, +64) A lo; the weights of all layers stay resident in shared memory (96 KiB per CTA).
+//
+// What changed against v3, and why (profiles/r2a_edge_v3_instruction_mix.txt: v3 executes 36.1k warp instructions per
+// 128-edge slot = 9.0k per scheduler against an HBM-bound slot time of 6.7k cycles — it is bound by instruction ISSUE):
+//   * regular streams ride the TMA engine (measured: 2.74 -> 2.46 ms at 1M targets, k = 6, 3 layers): e and P_c[tgt]
+//     arrive as tensor tiles (box 16 x 1 x 32 of the [N, k, 128] view of e, box 16 x 32 of P_c, SWIZZLE_64B) on a
+//     per-warp, per-stage mbarrier, only the gathered P_r[src] pieces stay on cp.async; e' leaves through a SWIZZLE_32B
+//     staging tile and cp.async.bulk.tensor stores (no STG.256 that touches 32 lines per instruction);
+//   * every elementwise stage works on packed fp32 pairs (FFMA2 / FADD2 / FMUL2, f32x2.cuh);
+//   * hidden activations are kept as SELU(x) / (lambda ln 2): the positive branch is the log2-domain pre-activation
+//     itself (no multiply), the constant rides on the next layer's 1/s;
+//   * LayerNorm output = FFMA2(FFMA2(y, rstd, -mean rstd), gamma', beta') with gamma' = gamma log2(e), beta' = beta
+//     log2(e) when the SELU of the model (nn/mus_gnn.py:321) follows, so the result is already the exponent's argument;
+//     the aggregation accumulates that scaled value and is un-scaled once per unit;
+//   * the loaders wait for "accumulator released" on a hardware named barrier (bar.arrive by the 16 epilogue warps,
+//     bar.sync by the 8 loader warps) instead of polling an mbarrier (v3: 3.5k polling instructions per slot);
+//   * P_r / P_c may arrive pre-multiplied by the layer-1 scale (p_scale == 1: no multiply in the loaders).
 #include <algorithm>
 #include <cstddef>
-#include <cstdlib>
 #include <cuda.h>
 #include "tc2_core.cuh"
+#include "f32x2.cuh"
 #include "mp_pair.h"
 
 namespace g4c {
-namespace ep4 {
+namespace ep5 {
 
 using namespace tc2;
+using namespace p2;
 
 constexpr int H = 128;
 constexpr int HIMG = 64 * 128;
@@ -43,37 +45,38 @@ constexpr int NT = 896;                  // warps 0-15 epilogue, 16-23 loaders, 
 constexpr int N_EPI_WARPS = 16;
 constexpr int N_LOAD_WARPS = 8;
 constexpr int W_LOAD0 = 16, W_MMA = 24;
-constexpr int kRegsMisc = 24;       // epilogue / loader registers are template parameters of the kernel (88 / 64 as in v3, or 96 / 48)
+constexpr int kRegsEpi = 88, kRegsLoad = 64, kRegsMisc = 24;
+static_assert(512 * kRegsEpi + 256 * kRegsLoad + 128 * kRegsMisc <= 896 * 72, "register budget");
 
 constexpr int SCOLS = 16;                // columns per loader stage
 constexpr int NCS = H / SCOLS;
-constexpr int NCS_W = NCS / 2;           // stages per slot per loader warp
-constexpr int ARR = 32 * 64;             // one array's 32 row pieces of a stage: 64-byte pitch, XOR swizzled
+constexpr int NCS_W = NCS / 2;           // stages per slot per loader warp (the two warps of a lane quarter alternate)
+constexpr int ARR = 32 * 64;             // one array's 32 row pieces of a stage: 64-byte pitch, SWIZZLE_64B
 constexpr int STG = 3 * ARR;             // e | P_r | P_c
 constexpr int NSTG = 2;
 constexpr int OPIECE = 32 * 32;          // e' staging of one epilogue warp: 32 rows x 8 columns, SWIZZLE_32B
+constexpr int BAR_DFREE0 = 6;                   // named barriers: 1-4 lane quarters, 5 all epilogue warps, 6 / 7 accumulator released
 
 constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
+constexpr float kA = kSeluAlpha * kLog2e;            // SELU(x) / (lambda ln 2) = t > 0 ? t : kA 2^t - kA,  t = x log2(e)
 
 struct Maps {
     CUtensorMap e_in;                    // [N, k, 128] fp32, box 16 x 1 x 32, SWIZZLE_64B
     CUtensorMap p_c;                     // [N, 128] fp32, box 16 x 32, SWIZZLE_64B
     CUtensorMap e_out;                   // [N, k, 128] fp32, box 8 x 1 x 32, SWIZZLE_32B
-    CUtensorMap p_r;                     // [*, 128] fp32, box 16 x 1 (tile::gather4: four rows per copy), SWIZZLE_64B
 };
 
 struct Smem {
     uint8_t w[3][4 * HIMG];                          // 96 KiB, 1024-byte aligned (UMMA SWIZZLE_128B images)
-    uint8_t ring[N_LOAD_WARPS][NSTG][STG];           // 96 KiB, every array 2048-byte aligned (SWIZZLE_64B repeats every 512 B)
-    uint8_t ostage[N_EPI_WARPS][OPIECE];             // 16 KiB, 1024-byte aligned (SWIZZLE_32B repeats every 256 B)
-    float cst[5][H];
-    float part[2][2][4][H];
+    uint8_t ring[N_LOAD_WARPS][NSTG][STG];           // 96 KiB, every array 2048-byte aligned
+    uint8_t ostage[N_EPI_WARPS][OPIECE];             // 16 KiB, 1024-byte aligned
+    float cst[5][H];                                 // [l] bias of layer l (hidden: times log2 e), [3] gamma', [4] beta'
+    float part[2][2][4][H];                          // LayerNorm partials [buffer][mean | M2][column quarter][row]
     uint64_t w_full;
-    uint64_t in_ready[2];
-    uint64_t a_ready[2];
-    uint64_t d_free[2];
-    uint64_t d_full[2];
-    uint64_t ld_full[N_LOAD_WARPS][NSTG];            // mode 2: the two TMA tiles of a loader stage have landed
+    uint64_t in_ready[2];                            // leader: A operand + initial accumulator of chain c written
+    uint64_t a_ready[2];                             // leader: next layer's A operand written
+    uint64_t d_full[2];                              // local, multicast commit
+    uint64_t ld_full[N_LOAD_WARPS][NSTG];            // the two TMA tiles of a loader stage have landed
     uint32_t tmem_base;
 };
 static_assert(sizeof(Smem) <= 232448, "shared memory exceeds the 227 KiB opt-in limit");
@@ -108,17 +111,12 @@ __device__ __forceinline__ void sts_f4(uint32_t addr, float x, float y, float z,
 }
 __device__ __forceinline__ void epi_sync_all() { asm volatile("bar.sync 5, 512;" ::: "memory"); }
 __device__ __forceinline__ void quarter_sync(int lq) { asm volatile("bar.sync %0, 128;" ::"r"(1 + lq) : "memory"); }
+// "accumulator of chain c released": 16 epilogue warps arrive, 8 loader warps wait (no polling, no issue slots while waiting)
+__device__ __forceinline__ void dfree_arrive(int c) { asm volatile("bar.arrive %0, 768;" ::"r"(BAR_DFREE0 + c) : "memory"); }
+__device__ __forceinline__ void dfree_wait(int c) { asm volatile("bar.sync %0, 768;" ::"r"(BAR_DFREE0 + c) : "memory"); }
 
-__device__ __forceinline__ float selu_over_lambda_l2(float t) {
-    float e;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
-    const float neg = fmaf(kSeluAlpha, e, -kSeluAlpha);
-    return t > 0.f ? t * kLn2 : neg;
-}
-
-// Sleeping mbarrier wait with a tighter watchdog than tc2_core.cuh's (2^24 polls x 20 us): a protocol error in this
-// not-yet-run kernel traps after about five seconds instead of minutes.  Hides tc2::mbar_wait_sleep_a inside this namespace.
-__device__ __forceinline__ void mbar_wait_sleep_a(uint32_t addr, uint32_t parity) {
+// sleeping mbarrier wait with a short watchdog (a protocol error traps after seconds instead of hanging the GPU)
+__device__ __forceinline__ void mbar_wait_sleep_w(uint32_t addr, uint32_t parity) {
     uint32_t spins = 0, ok;
     do {
         asm volatile(
@@ -126,7 +124,7 @@ __device__ __forceinline__ void mbar_wait_sleep_a(uint32_t addr, uint32_t parity
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}\n"
             : "=r"(ok) : "r"(addr), "r"(parity), "r"(20000u) : "memory");
-        if (!ok && ++spins > (1u << 18)) __trap();
+        if (!ok && ++spins > (1u << 20)) __trap();
     } while (!ok);
 }
 
@@ -142,26 +140,15 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, 
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                  ::"r"(dst), "l"(m), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
-// four rows r0..r3 of a 2-D tensor, box_cols columns from c0 each, to four consecutive row pieces at dst
-__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* m, int c0, int r0, int r1, int r2, int r3, uint32_t bar) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
-                 ::"r"(dst), "l"(m), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar) : "memory");
-}
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, int c0, int c1, int c2, uint32_t src) {
     asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];"
                  ::"l"(m), "r"(c0), "r"(c1), "r"(c2), "r"(src) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-// every bulk group this thread committed has finished READING its shared-memory source
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-// ... all but the most recent one
 __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 
-// kLoad: 0 = every row piece by cp.async (mode 1), 1 = e / P_c tiles by TMA (mode 2), 2 = P_r[src] by TMA gather4 as well (mode 3)
-template <int kLoad, int kRegsEpi = 88, int kRegsLoad = 64>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_tma_kernel(const EdgeArgs a, const __grid_constant__ Maps tm) {
-    constexpr bool kTmaLoad = kLoad >= 1, kGather = kLoad == 2;
-    static_assert(512 * kRegsEpi + 256 * kRegsLoad + 128 * kRegsMisc <= 896 * 72, "register budget");
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_v5_kernel(const EdgeArgs a, const __grid_constant__ Maps tm) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     Smem& s = *reinterpret_cast<Smem*>(smem_raw);
     if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
@@ -173,13 +160,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_tma_kern
     const int n_units = (int)((a.n_targets + 127) / 128);
     const int n_up = (n_units + 1) / 2;
     const int up0 = blockIdx.x >> 1, up_stride = gridDim.x >> 1;
+    // the SELU that the models apply to a block's edge output: fold log2(e) into the LayerNorm affine
+    const bool selu_out = a.e_out != nullptr && a.act_e_out == G4C_ACT_SELU;
+    const float fold = selu_out ? kLog2e : 1.f;
 
     if (tid == 0) {
         mbar_init(&s.w_full, 1);
         for (int c = 0; c < 2; ++c) {
             mbar_init(&s.in_ready[c], 2 * N_LOAD_WARPS);
             mbar_init(&s.a_ready[c], 2 * N_EPI_WARPS);
-            mbar_init(&s.d_free[c], N_EPI_WARPS);
             mbar_init(&s.d_full[c], 1);
         }
         for (int w = 0; w < N_LOAD_WARPS; ++w)
@@ -197,8 +186,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_tma_kern
             if (l > 0 && l < nl) b = a.bias[l][tid] * (l < nl - 1 ? kLog2e : 1.f);
             s.cst[l][tid] = b;
         }
-        s.cst[3][tid] = a.gamma ? a.gamma[tid] : 1.f;
-        s.cst[4][tid] = a.beta ? a.beta[tid] : 0.f;
+        s.cst[3][tid] = (a.gamma ? a.gamma[tid] : 1.f) * fold;
+        s.cst[4][tid] = (a.beta ? a.beta[tid] : 0.f) * fold;
     }
     tc_fence_before();
     cluster_sync_all();
@@ -207,7 +196,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_tma_kern
     const uint32_t sb = smem_u32(smem_raw);
     const uint32_t a_cst = sb + (uint32_t)offsetof(Smem, cst), a_part = sb + (uint32_t)offsetof(Smem, part);
     const uint32_t a_in_ready = sb + (uint32_t)offsetof(Smem, in_ready), a_a_ready = sb + (uint32_t)offsetof(Smem, a_ready);
-    const uint32_t a_d_free = sb + (uint32_t)offsetof(Smem, d_free), a_d_full = sb + (uint32_t)offsetof(Smem, d_full);
+    const uint32_t a_d_full = sb + (uint32_t)offsetof(Smem, d_full);
 
     if (warp < N_EPI_WARPS) {
         // ====================================================================== epilogue warps
@@ -220,17 +209,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_tma_kern
         const uint32_t leader_a_ready0 = mapa(a_a_ready, 0);
         const uint32_t my_cst = a_cst + 128u * cq, my_part = a_part + 4u * row;
         // e' staging of this warp: row = lane at a 32-byte pitch, 16-byte chunk c at c ^ ((lane >> 2) & 1)  (SWIZZLE_32B)
-        // (tile base = ost0 & ~1023, the other chunk = ost0 ^ 16: one live register)
         const uint32_t ost0 = sb + (uint32_t)offsetof(Smem, ostage) + (uint32_t)(etid >> 5) * OPIECE + (uint32_t)lane * 32u +
                               ((uint32_t)((lane >> 2) & 1) << 4);
-        // lane 0 issues, commits and waits for every bulk store of this warp (bulk groups are per thread).
-        // Two-layer MLPs (REMuS angle / edge models) leave the third layer's 32 KiB of weight space unused: there the staging is
-        // double buffered (pieces alternate between two 1 KiB tiles per warp, the wait lets one store stay in flight).
+        // two-layer MLPs (REMuS) leave the third layer's 32 KiB of weight space unused: staging is double buffered there
         const bool two_buf = nl == 2;
         const uint32_t ost_alt = sb + (uint32_t)offsetof(Smem, w) + 2u * 4u * HIMG + (uint32_t)(etid >> 5) * (2u * OPIECE) +
                                  (uint32_t)lane * 32u + ((uint32_t)((lane >> 2) & 1) << 4);
         uint32_t n_dfull[2] = {0, 0};
         const bool has_ln = a.gamma != nullptr;
+        const bool want_e = a.e_out != nullptr;
         int pbuf = 0;
         PROF_DECL
         PROF_START();
@@ -238,25 +225,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_tma_kern
         for (int up = up0; up < n_up; up += up_stride) {
             const int n_unit0 = (up * 2 + (int)rank) * 128;         // n_targets < 2^31 (checked by g4c_edge_aggr_fwd)
             const bool live = n_unit0 + row < a.n_targets;
-            float agg[32];
+            uint64_t agg[16];                                       // 32 columns as pairs, in units of `fold`
 #pragma unroll
-            for (int i = 0; i < 32; ++i) agg[i] = 0.f;
+            for (int i = 0; i < 16; ++i) agg[i] = 0ull;
 
             for (int j0 = 0; j0 < k; j0 += 2) {
                 const int nch = min(2, k - j0);
                 for (int l = 0; l < nl; ++l) {
-                    const float cl = a.inv_scale[l] * (l > 0 ? kSeluScale : 1.f);
+                    // scale of this layer's accumulator: 1/s, times lambda ln 2 when its input was a deferred-constant SELU
+                    const float cl = a.inv_scale[l] * (l > 0 ? kSeluScale * kLn2 : 1.f);
 #pragma unroll
                     for (int c = 0; c < 2; ++c) {
                         if (c >= nch) continue;
                         const uint32_t d_addr = tmem + lane_base + 256u * c + 32u * cq;
-                        if (warp == 0) mbar_wait_sleep_a(a_d_full + 8u * c, n_dfull[c] & 1);
+                        if (warp == 0) mbar_wait_sleep_w(a_d_full + 8u * c, n_dfull[c] & 1);
                         ++n_dfull[c];
                         epi_sync_all();
                         tc_fence_after();
                         PROF_LAP(l < nl - 1 ? 0 : 1);        // waiting for the MMAs (hidden / last layer)
                         if (l < nl - 1) {
-                            const float c2 = cl * kLog2e;
+                            // ---- hidden layer: x'' = SELU(acc cl + b) / (lambda ln 2) as fp16 (hi, lo) A operand columns
+                            const uint64_t c2 = bc(cl * kLog2e), pA = bc(kA), nA = bc(-kA);
 #pragma unroll
                             for (int h16 = 0; h16 < 2; ++h16) {
                                 float v[16];
@@ -266,12 +255,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_tma_kern
 #pragma unroll
                                 for (int i = 0; i < 16; i += 4) {
                                     const float4 b = lds_f4(bs + 4u * i);
-                                    const float x0 = selu_over_lambda_l2(fmaf(v[i], c2, b.x));
-                                    const float x1 = selu_over_lambda_l2(fmaf(v[i + 1], c2, b.y));
-                                    const float x2 = selu_over_lambda_l2(fmaf(v[i + 2], c2, b.z));
-                                    const float x3 = selu_over_lambda_l2(fmaf(v[i + 3], c2, b.w));
-                                    split2(x0, x1, hi[i / 2], lo[i / 2]);
-                                    split2(x2, x3, hi[i / 2 + 1], lo[i / 2 + 1]);
+                                    float t0, t1, t2, t3, n0, n1, n2, n3;
+                                    upk(fma2(pk(v[i], v[i + 1]), c2, pk(b.x, b.y)), t0, t1);
+                                    upk(fma2(pk(v[i + 2], v[i + 3]), c2, pk(b.z, b.w)), t2, t3);
+                                    upk(fma2(pk(ex2(t0), ex2(t1)), pA, nA), n0, n1);
+                                    upk(fma2(pk(ex2(t2), ex2(t3)), pA, nA), n2, n3);
+                                    split_pair(t0 > 0.f ? t0 : n0, t1 > 0.f ? t1 : n1, hi[i / 2], lo[i / 2]);
+                                    split_pair(t2 > 0.f ? t2 : n2, t3 > 0.f ? t3 : n3, hi[i / 2 + 1], lo[i / 2 + 1]);
                                 }
                                 tmem_st8(tmem + lane_base + 256u * c + 128u + 16u * cq + 8u * h16, hi);
                                 tmem_st8(tmem + lane_base + 256u * c + 192u + 16u * cq + 8u * h16, lo);
@@ -282,44 +272,46 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_tma_kern
                             if (lane == 0) mbar_arrive_remote(leader_a_ready0 + 8u * c);
                             PROF_LAP(2);                     // hidden epilogue
                         } else {
+                            // ---- last layer: LayerNorm, aggregation, store.  The accumulator is read once and released at once.
                             const uint32_t bs = my_cst + 512u * l;
                             float y[32];
                             tmem_ld16_nowait(d_addr, y);
                             tmem_ld16_nowait(d_addr + 16u, y + 16);
                             tmem_wait_ld();
                             tc_fence_before();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive_a(a_d_free + 8u * c);
+                            dfree_arrive(c);
+                            uint64_t yp[16];
+                            const uint64_t clp = bc(cl);
 #pragma unroll
                             for (int i = 0; i < 32; i += 4) {
                                 const float4 b4 = lds_f4(bs + 4u * i);
-                                y[i] = fmaf(y[i], cl, b4.x);
-                                y[i + 1] = fmaf(y[i + 1], cl, b4.y);
-                                y[i + 2] = fmaf(y[i + 2], cl, b4.z);
-                                y[i + 3] = fmaf(y[i + 3], cl, b4.w);
+                                yp[i / 2] = fma2(pk(y[i], y[i + 1]), clp, pk(b4.x, b4.y));
+                                yp[i / 2 + 1] = fma2(pk(y[i + 2], y[i + 3]), clp, pk(b4.z, b4.w));
                             }
                             float mean = 0.f, rstd = 1.f;
                             if (has_ln) {
                                 float mh[2], M2h[2];
 #pragma unroll
                                 for (int h16 = 0; h16 < 2; ++h16) {
-                                    float sum = 0.f;
+                                    const uint64_t* p = yp + 8 * h16;
+                                    float s0, s1;
+                                    upk(add2(add2(add2(p[0], p[1]), add2(p[2], p[3])), add2(add2(p[4], p[5]), add2(p[6], p[7]))), s0, s1);
+                                    mh[h16] = (s0 + s1) * (1.f / 16.f);
+                                    const uint64_t mp = bc(mh[h16]);
+                                    uint64_t q0 = 0ull, q1 = 0ull;
 #pragma unroll
-                                    for (int i = 0; i < 16; i += 4)
-                                        sum += (y[16 * h16 + i] + y[16 * h16 + i + 1]) + (y[16 * h16 + i + 2] + y[16 * h16 + i + 3]);
-                                    mh[h16] = sum * (1.f / 16.f);
-                                    float sq = 0.f;
-#pragma unroll
-                                    for (int i = 0; i < 16; ++i) {
-                                        const float dlt = y[16 * h16 + i] - mh[h16];
-                                        sq = fmaf(dlt, dlt, sq);
+                                    for (int i = 0; i < 8; i += 2) {
+                                        const uint64_t d0 = sub2(p[i], mp), d1 = sub2(p[i + 1], mp);
+                                        q0 = fma2(d0, d0, q0);
+                                        q1 = fma2(d1, d1, q1);
                                     }
-                                    M2h[h16] = sq;
+                                    upk(add2(q0, q1), s0, s1);
+                                    M2h[h16] = s0 + s1;
                                 }
                                 const float dm = mh[0] - mh[1];
                                 const uint32_t pa = my_part + 4096u * pbuf;
-                                sts_f1(pa + 512u * cq, 0.5f * (mh[0] + mh[1]));
-                                sts_f1(pa + 2048u + 512u * cq, (M2h[0] + M2h[1]) + 8.f * dm * dm);
+                                sts_f1(pa + 512u * cq, 0.5f * (mh[0] + mh[1]));                       // mean of this thread's 32 columns
+                                sts_f1(pa + 2048u + 512u * cq, (M2h[0] + M2h[1]) + 8.f * dm * dm);     // their M2 (Chan)
                                 PROF_LAP(3);                 // last layer: read + statistics
                                 quarter_sync(lq);
                                 PROF_LAP(4);                 // last layer: barrier
@@ -331,39 +323,47 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_tma_kern
                                 rstd = 1.f / sqrtf(M2 * (1.f / H) + kLnEps);
                                 pbuf ^= 1;
                             }
+                            const uint64_t rs = bc(rstd), nm = bc(-mean * rstd);
+                            const uint64_t lp = bc(kSeluScale * kLn2), sa = bc(kSeluScale * kSeluAlpha), nsa = bc(-kSeluScale * kSeluAlpha);
                             const int j = j0 + c;
 #pragma unroll
                             for (int i8 = 0; i8 < 32; i8 += 8) {
-                                float* o = y + i8;
-                                if (has_ln) {
+                                // o = fold * LN(y): normalise, affine (gamma', beta' carry `fold`), aggregate
+                                uint64_t o[4];
 #pragma unroll
-                                    for (int u = 0; u < 8; u += 4) {
-                                        const float4 g = lds_f4(my_cst + 1536u + 4u * (i8 + u));
-                                        const float4 be = lds_f4(my_cst + 2048u + 4u * (i8 + u));
-                                        o[u] = fmaf((o[u] - mean) * rstd, g.x, be.x);
-                                        o[u + 1] = fmaf((o[u + 1] - mean) * rstd, g.y, be.y);
-                                        o[u + 2] = fmaf((o[u + 2] - mean) * rstd, g.z, be.z);
-                                        o[u + 3] = fmaf((o[u + 3] - mean) * rstd, g.w, be.w);
-                                    }
+                                for (int u = 0; u < 2; ++u) {
+                                    const float4 g = lds_f4(my_cst + 1536u + 4u * (i8 + 4 * u));
+                                    const float4 be = lds_f4(my_cst + 2048u + 4u * (i8 + 4 * u));
+                                    o[2 * u] = fma2(fma2(yp[i8 / 2 + 2 * u], rs, nm), pk(g.x, g.y), pk(be.x, be.y));
+                                    o[2 * u + 1] = fma2(fma2(yp[i8 / 2 + 2 * u + 1], rs, nm), pk(g.z, g.w), pk(be.z, be.w));
                                 }
-                                if (live) {
 #pragma unroll
-                                    for (int u = 0; u < 8; ++u) agg[i8 + u] += o[u];
-                                }
-                                if (a.e_out != nullptr) {       // warp-uniform
-                                    if (a.act_e_out == G4C_ACT_SELU) {
+                                for (int u = 0; u < 4; ++u) agg[i8 / 2 + u] = add2(agg[i8 / 2 + u], o[u]);
+                                if (want_e) {                   // warp-uniform
+                                    float r[8];
+                                    if (selu_out) {
+                                        // lambda SELU(x) from t = x log2 e: t > 0 ? t lambda ln 2 : lambda alpha 2^t - lambda alpha
 #pragma unroll
-                                        for (int u = 0; u < 8; ++u) o[u] = selu_fast(o[u]);
+                                        for (int u = 0; u < 4; ++u) {
+                                            float t0, t1, p0, p1, n0, n1;
+                                            upk(o[u], t0, t1);
+                                            upk(mul2(o[u], lp), p0, p1);
+                                            upk(fma2(pk(ex2(t0), ex2(t1)), sa, nsa), n0, n1);
+                                            r[2 * u] = t0 > 0.f ? p0 : n0;
+                                            r[2 * u + 1] = t1 > 0.f ? p1 : n1;
+                                        }
+                                    } else {
+#pragma unroll
+                                        for (int u = 0; u < 4; ++u) upk(o[u], r[2 * u], r[2 * u + 1]);
                                     }
-                                    // the staging tile is free once the previous piece's bulk store has read it; everything above
-                                    // (normalise, aggregate, SELU of this piece) ran while the TMA engine was reading
+                                    // the staging tile is free once the previous piece's bulk store has read it
                                     const uint32_t ost = two_buf ? ost_alt + (uint32_t)((i8 >> 3) & 1) * OPIECE : ost0;
                                     if (lane == 0) {
                                         if (two_buf) bulk_wait_read1(); else bulk_wait_read0();
                                     }
                                     __syncwarp();
-                                    sts_f4(ost, o[0], o[1], o[2], o[3]);
-                                    sts_f4(ost ^ 16u, o[4], o[5], o[6], o[7]);
+                                    sts_f4(ost, r[0], r[1], r[2], r[3]);
+                                    sts_f4(ost ^ 16u, r[4], r[5], r[6], r[7]);
                                     fence_proxy_async();        // generic-proxy writes -> visible to the TMA engine
                                     __syncwarp();
                                     // rows past the last target hold values of no edge; the tensor map's bounds clip them
@@ -379,13 +379,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_tma_kern
                 }
             }
             if (live) {
-                const float rc = (a.aggr == G4C_AGGR_MEAN) ? 1.f / (float)max(k, 1) : 1.f;
+                const float rc = ((a.aggr == G4C_AGGR_MEAN) ? 1.f / (float)max(k, 1) : 1.f) / fold;
                 float* dst = a.agg_out + (size_t)(n_unit0 + row) * H + cq * 32;
+                const uint64_t rcp = bc(rc);
 #pragma unroll
                 for (int i = 0; i < 32; i += 8) {
                     float o[8];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) o[u] = agg[i + u] * rc;
+                    for (int u = 0; u < 4; ++u) upk(mul2(agg[i / 2 + u], rcp), o[2 * u], o[2 * u + 1]);
                     stg256(dst + i, o);
                 }
             }
@@ -397,6 +398,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_tma_kern
         setmaxnreg_dec<kRegsLoad>();
         const int lw = (warp - W_LOAD0) & 3, hf = (warp - W_LOAD0) >> 2;
         const float ps = a.p_scale;
+        const bool scale_p = ps != 1.f;
+        const uint64_t psp = bc(ps);
         const uint32_t lane_base = (uint32_t)(lw * 32) << 16;
         const uint32_t ring0 = smem_u32(s.ring[warp - W_LOAD0][0]);
         const uint32_t bar0 = smem_u32(&s.ld_full[warp - W_LOAD0][0]);
@@ -407,37 +410,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_tma_kern
         // term (row >> 1) & 3 does not depend on i
         const uint32_t dst_off = (uint32_t)sub * 64u + ((uint32_t)(piece ^ ((sub >> 1) & 3)) << 4);
         const bool leader = elect_one();
-        mbar_wait(&s.w_full, 0);
+        mbar_wait(&s.w_full, 0);           // in_ready is only signalled once this CTA's weights have landed
 
+        // ---- issue cursor: runs NSTG-1 stages ahead of the processing cursor
         int i_up = up0;
         int i_j = 0, i_cs = 0;
         int64_t i_n = -1;                 // this lane's target in the unit pair being issued, -1: none
         int nx_srow = -1;
-        uint32_t oe[4], os[4], ot[4], vmask = 0;
-        int gr[4] = {0, 0, 0, 0};         // kGather: lanes 0-7 hold the source rows of tile rows 4 lane .. 4 lane + 3
+        uint32_t os[4], vmask = 0;        // offsets (16-byte units) of this lane's piece in the four source rows it copies
         bool i_live = false;
         auto load_src = [&](int j) -> int {               // source row of the j-th in-edge of this lane's target
             return (i_n >= 0 && j < k) ? __ldg(a.src + i_n * k + j) : -1;
         };
-        auto spread_slot = [&](int j, int srow) {
+        auto spread_slot = [&](int srow) {
             vmask = 0;
-            if (kGather) {
-                // a tile row without an edge reads row 0 of P_r: its accumulator row is never stored (rows are independent
-                // through the MMAs and the LayerNorm; agg is skipped and the e' store is clipped for it)
 #pragma unroll
-                for (int i = 0; i < 4; ++i) gr[i] = max(__shfl_sync(0xffffffffu, srow, (4 * lane + i) & 31), 0);
-            } else {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int sr = __shfl_sync(0xffffffffu, srow, 8 * i + sub);
-                    const bool ok = sr >= 0;
-                    vmask |= ok ? (1u << i) : 0u;
-                    os[i] = ok ? (uint32_t)sr * 32u + piece : 0u;
-                    if (!kTmaLoad) {
-                        const long long er = __shfl_sync(0xffffffffu, (long long)(i_n >= 0 ? i_n * k + j : -1), 8 * i + sub);
-                        oe[i] = ok ? (uint32_t)er * 32u + piece : 0u;
-                    }
-                }
+            for (int i = 0; i < 4; ++i) {
+                const int sr = __shfl_sync(0xffffffffu, srow, 8 * i + sub);
+                const bool ok = sr >= 0;
+                vmask |= ok ? (1u << i) : 0u;
+                os[i] = ok ? (uint32_t)sr * 32u + piece : 0u;
             }
         };
         auto seek_unit = [&]() {
@@ -446,14 +438,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_tma_kern
                 const int64_t n = (int64_t)i_up * 256 + row_in_pair;
                 i_n = n < a.n_targets ? n : -1;
                 i_j = 0; i_cs = 0;
-                if (!kTmaLoad) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const long long tr = __shfl_sync(0xffffffffu, (long long)i_n, 8 * i + sub);
-                        ot[i] = tr >= 0 ? (uint32_t)tr * 32u + piece : 0u;
-                    }
-                }
-                spread_slot(0, load_src(0));
+                spread_slot(load_src(0));
             }
         };
         auto issue_stage = [&](uint32_t stage_addr, uint32_t bar_addr) {
@@ -465,70 +450,32 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_tma_kern
                 uint32_t sz[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    sz[i] = (vmask >> i) & 1u ? 16u : 0u;
+                    sz[i] = (vmask >> i) & 1u ? 16u : 0u;        // 0: nothing is read, the destination is zero-filled
                     pr[i] = reinterpret_cast<const float*>(br + (size_t)os[i] * 16);
                 }
-                if (kGather) {
+                asm volatile(
+                    "cp.async.cg.shared.global [%0 + 2048], [%1], 16, %5;\n\t"
+                    "cp.async.cg.shared.global [%0 + 2560], [%2], 16, %6;\n\t"
+                    "cp.async.cg.shared.global [%0 + 3072], [%3], 16, %7;\n\t"
+                    "cp.async.cg.shared.global [%0 + 3584], [%4], 16, %8;\n"
+                    ::"r"(dst0), "l"(pr[0]), "l"(pr[1]), "l"(pr[2]), "l"(pr[3]), "r"(sz[0]), "r"(sz[1]), "r"(sz[2]), "r"(sz[3])
+                    : "memory");
+                static_assert(ARR == 2048 && STG == 6144, "offsets in the cp.async block above");
+                if (leader) {
+                    // rows past the last target are zero-filled by the tensor maps' bounds (and count towards the bytes)
                     const int n0w = (i_up * 2 + (int)rank) * 128 + lw * 32;
-                    if (leader) {
-                        mbar_arrive_expect_tx_a(bar_addr, 3 * ARR);
-                        tma_load_3d(stage_addr, &tm.e_in, col0, i_j, n0w, bar_addr);
-                        tma_load_2d(stage_addr + 2 * ARR, &tm.p_c, col0, n0w, bar_addr);
-                    }
-                    __syncwarp();
-                    // eight copies of four gathered rows each; divergent operands: ptxas serialises the lanes (R2UR + BRA.U.ANY)
-                    if (lane < 8) tma_gather4(stage_addr + ARR + 256u * lane, &tm.p_r, col0, gr[0], gr[1], gr[2], gr[3], bar_addr);
-                } else if (kTmaLoad) {
-                    asm volatile(
-                        "cp.async.cg.shared.global [%0 + 2048], [%1], 16, %5;\n\t"
-                        "cp.async.cg.shared.global [%0 + 2560], [%2], 16, %6;\n\t"
-                        "cp.async.cg.shared.global [%0 + 3072], [%3], 16, %7;\n\t"
-                        "cp.async.cg.shared.global [%0 + 3584], [%4], 16, %8;\n"
-                        ::"r"(dst0), "l"(pr[0]), "l"(pr[1]), "l"(pr[2]), "l"(pr[3]), "r"(sz[0]), "r"(sz[1]), "r"(sz[2]), "r"(sz[3])
-                        : "memory");
-                    if (leader) {
-                        // rows past the last target are zero-filled by the tensor maps' bounds (and count towards the bytes)
-                        const int n0w = (i_up * 2 + (int)rank) * 128 + lw * 32;
-                        mbar_arrive_expect_tx_a(bar_addr, 2 * ARR);
-                        tma_load_3d(stage_addr, &tm.e_in, col0, i_j, n0w, bar_addr);
-                        tma_load_2d(stage_addr + 2 * ARR, &tm.p_c, col0, n0w, bar_addr);
-                    }
-                } else {
-                    const char* be = reinterpret_cast<const char*>(a.e_in) + col0 * 4;
-                    const char* bc = reinterpret_cast<const char*>(a.P_c) + col0 * 4;
-                    const float* pe[4];
-                    const float* pc[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        pe[i] = reinterpret_cast<const float*>(be + (size_t)oe[i] * 16);
-                        pc[i] = reinterpret_cast<const float*>(bc + (size_t)ot[i] * 16);
-                    }
-                    asm volatile(
-                        "cp.async.cg.shared.global [%0], [%1], 16, %13;\n\t"
-                        "cp.async.cg.shared.global [%0 + 2048], [%2], 16, %13;\n\t"
-                        "cp.async.cg.shared.global [%0 + 4096], [%3], 16, %13;\n\t"
-                        "cp.async.cg.shared.global [%0 + 512], [%4], 16, %14;\n\t"
-                        "cp.async.cg.shared.global [%0 + 2560], [%5], 16, %14;\n\t"
-                        "cp.async.cg.shared.global [%0 + 4608], [%6], 16, %14;\n\t"
-                        "cp.async.cg.shared.global [%0 + 1024], [%7], 16, %15;\n\t"
-                        "cp.async.cg.shared.global [%0 + 3072], [%8], 16, %15;\n\t"
-                        "cp.async.cg.shared.global [%0 + 5120], [%9], 16, %15;\n\t"
-                        "cp.async.cg.shared.global [%0 + 1536], [%10], 16, %16;\n\t"
-                        "cp.async.cg.shared.global [%0 + 3584], [%11], 16, %16;\n\t"
-                        "cp.async.cg.shared.global [%0 + 5632], [%12], 16, %16;\n"
-                        ::"r"(dst0), "l"(pe[0]), "l"(pr[0]), "l"(pc[0]), "l"(pe[1]), "l"(pr[1]), "l"(pc[1]), "l"(pe[2]), "l"(pr[2]),
-                        "l"(pc[2]), "l"(pe[3]), "l"(pr[3]), "l"(pc[3]), "r"(sz[0]), "r"(sz[1]), "r"(sz[2]), "r"(sz[3])
-                        : "memory");
+                    mbar_arrive_expect_tx_a(bar_addr, 2 * ARR);
+                    tma_load_3d(stage_addr, &tm.e_in, col0, i_j, n0w, bar_addr);
+                    tma_load_2d(stage_addr + 2 * ARR, &tm.p_c, col0, n0w, bar_addr);
                 }
-                static_assert(ARR == 2048 && STG == 6144, "offsets in the cp.async blocks above");
                 if (++i_cs == 1) nx_srow = load_src(i_j + 1);               // source ids of the next slot: three stages of slack
                 if (i_cs == NCS_W) {
                     i_cs = 0;
-                    if (++i_j < k) spread_slot(i_j, nx_srow);
+                    if (++i_j < k) spread_slot(nx_srow);
                     else { i_up += up_stride; seek_unit(); }
                 }
             }
-            cp_async_commit();
+            cp_async_commit();              // one (possibly empty) group per stage keeps the wait depth constant
         };
 
         seek_unit();
@@ -536,7 +483,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_tma_kern
         for (int p = 0; p < NSTG - 1; ++p) issue_stage(ring0 + p * STG, bar0 + 8u * p);
         PROF_DECL
         PROF_START();
-        uint32_t q = 0, n_slot0 = 0, n_slot1 = 0;
+        uint32_t q = 0, n_slot0 = 0, n_slot1 = 0;      // slots filled per chain
         const uint32_t swz = (uint32_t)((lane >> 1) & 3);
         for (int up = up0; up < n_up; up += up_stride) {
             for (int j = 0; j < k; ++j) {
@@ -546,12 +493,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_tma_kern
                 for (int cw = 0; cw < NCS_W; ++cw, ++q) {
                     const int cs = 2 * cw + hf;
                     cp_async_wait<NSTG - 2>();                   // the cp.async part of stage q has landed
-                    if (kTmaLoad) mbar_wait_sleep_a(bar0 + 8u * (q % NSTG), (q / NSTG) & 1);      // ... and its two TMA tiles
+                    mbar_wait_sleep_w(bar0 + 8u * (q % NSTG), (q / NSTG) & 1);      // ... and its two TMA tiles
                     __syncwarp();
                     PROF_LAP(0);                                 // waiting for the staged rows
                     issue_stage(ring0 + ((q + NSTG - 1) % NSTG) * STG, bar0 + 8u * ((q + NSTG - 1) % NSTG));
                     if (cw == 0) {
-                        mbar_wait_sleep_a(a_d_free + 8u * cc, ((cc ? n_slot1 : n_slot0) + 1) & 1);
+                        // last-layer epilogue of the previous slot on this chain has read the accumulator
+                        if ((cc ? n_slot1 : n_slot0) > 0) dfree_wait(cc);
                         tc_fence_after();
                         PROF_LAP(1);                             // waiting for the accumulator to be released
                     }
@@ -569,16 +517,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_tma_kern
                         uint32_t eh[4], el[4], pp[8];
 #pragma unroll
                         for (int v4 = 0; v4 < 2; ++v4) {
-                            split2(xe[v4].x, xe[v4].y, eh[2 * v4], el[2 * v4]);
-                            split2(xe[v4].z, xe[v4].w, eh[2 * v4 + 1], el[2 * v4 + 1]);
-                            pp[4 * v4] = __float_as_uint((xr[v4].x + xc[v4].x) * ps);
-                            pp[4 * v4 + 1] = __float_as_uint((xr[v4].y + xc[v4].y) * ps);
-                            pp[4 * v4 + 2] = __float_as_uint((xr[v4].z + xc[v4].z) * ps);
-                            pp[4 * v4 + 3] = __float_as_uint((xr[v4].w + xc[v4].w) * ps);
+                            split_pair(xe[v4].x, xe[v4].y, eh[2 * v4], el[2 * v4]);
+                            split_pair(xe[v4].z, xe[v4].w, eh[2 * v4 + 1], el[2 * v4 + 1]);
+                            uint64_t p01 = add2(pk(xr[v4].x, xr[v4].y), pk(xc[v4].x, xc[v4].y));
+                            uint64_t p23 = add2(pk(xr[v4].z, xr[v4].w), pk(xc[v4].z, xc[v4].w));
+                            if (scale_p) { p01 = mul2(p01, psp); p23 = mul2(p23, psp); }
+                            upk_u(p01, pp[4 * v4], pp[4 * v4 + 1]);
+                            upk_u(p23, pp[4 * v4 + 2], pp[4 * v4 + 3]);
                         }
-                        tmem_st4(d_col + 128u + 8u * cs + 4u * h8, eh);
-                        tmem_st4(d_col + 192u + 8u * cs + 4u * h8, el);
-                        tmem_st8(d_col + 16u * cs + 8u * h8, pp);
+                        tmem_st4(d_col + 128u + 8u * cs + 4u * h8, eh);       // A hi: k = 16 cs + 8 h8 .. +7
+                        tmem_st4(d_col + 192u + 8u * cs + 4u * h8, el);       // A lo
+                        tmem_st8(d_col + 16u * cs + 8u * h8, pp);             // accumulator columns 16 cs + 8 h8 .. +7
                     }
                     if (cw == NCS_W - 1) {
                         tmem_wait_st();
@@ -594,6 +543,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_tma_kern
             }
         }
         cp_async_wait<0>();
+        // drain: the epilogue arrives once per slot, the loaders waited once per slot but the first of each chain
+        if (n_slot0 > 0) dfree_wait(0);
+        if (n_slot1 > 0) dfree_wait(1);
         PROF_FLUSH(8, warp == W_LOAD0);
     } else {
         setmaxnreg_dec<kRegsMisc>();
@@ -612,13 +564,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_tma_kern
                             const uint32_t d_col = tmem + 256u * c, ah = d_col + 128u, al = d_col + 192u;
                             if (l == 0) {
                                 if (lane == 0) {
-                                    mbar_wait_sleep_a(a_in_ready + 8u * c, n_chain[c] & 1);
+                                    mbar_wait_sleep_w(a_in_ready + 8u * c, n_chain[c] & 1);
                                     tc_fence_after();
                                 }
                                 ++n_chain[c];
                             } else {
                                 if (lane == 0) {
-                                    mbar_wait_sleep_a(a_a_ready + 8u * c, n_ar[c] & 1);
+                                    mbar_wait_sleep_w(a_a_ready + 8u * c, n_ar[c] & 1);
                                     tc_fence_after();
                                 }
                                 ++n_ar[c];
@@ -644,7 +596,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT, 1) edge_tma_kern
     }
 
     // shared memory must outlive the last bulk store's read.  (Placed here and not at the end of the epilogue role: code
-    // after that role's unit loop makes ptxas spill 16 of the agg[] registers.)
+    // after that role's unit loop makes ptxas spill accumulator registers.)
     if (warp < N_EPI_WARPS && (tid & 31) == 0) bulk_wait_read0();
     tc_fence_before();
     cluster_sync_all();
@@ -671,10 +623,12 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// fp32 view [rows, (k,) 128] of a row-major feature matrix; box = box_cols x (1 x) box_rows
-static bool encode(CUtensorMap* m, const float* base, int64_t rows, int k, int box_cols, CUtensorMapSwizzle swz, int box_rows = 32) {
+// fp32 view [rows, (k,) 128] of a row-major feature matrix; box = box_cols x (1 x) box_rows; swizzle in bytes (32 / 64 / 128)
+bool encode_rows(CUtensorMap* m, const float* base, int64_t rows, int k, int box_cols, int swizzle_bytes, int box_rows) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
+    const CUtensorMapSwizzle swz = swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                                                                      : CU_TENSOR_MAP_SWIZZLE_128B;
     const cuuint32_t ones[3] = {1, 1, 1};
     CUresult r;
     if (k > 0) {
@@ -693,20 +647,13 @@ static bool encode(CUtensorMap* m, const float* base, int64_t rows, int k, int b
     return r == CUDA_SUCCESS;
 }
 
-// the same, callable from tma_test.cu (swizzle given in bytes: 32 / 64 / 128)
-bool encode_rows(CUtensorMap* m, const float* base, int64_t rows, int k, int box_cols, int swizzle_bytes, int box_rows) {
-    const CUtensorMapSwizzle swz = swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
-                                                                                                      : CU_TENSOR_MAP_SWIZZLE_128B;
-    return encode(m, base, rows, k, box_cols, swz, box_rows);
-}
+}  // namespace ep5
 
-}  // namespace ep4
-
-int edge_pair_tma_profile(unsigned long long* out64) {
+int edge_v5_profile(unsigned long long* out64) {
 #ifdef G4C_PROFILE
-    if (cudaMemcpyFromSymbol(out64, ep4::g_prof, sizeof(unsigned long long) * 64) != cudaSuccess) return check_launch("profile read");
+    if (cudaMemcpyFromSymbol(out64, ep5::g_prof, sizeof(unsigned long long) * 64) != cudaSuccess) return check_launch("profile read");
     unsigned long long zero[64] = {0};
-    cudaMemcpyToSymbol(ep4::g_prof, zero, sizeof(zero));
+    cudaMemcpyToSymbol(ep5::g_prof, zero, sizeof(zero));
     return G4C_OK;
 #else
     (void)out64;
@@ -715,59 +662,27 @@ int edge_pair_tma_profile(unsigned long long* out64) {
 #endif
 }
 
-static int g_edge_mode = -1;      // -1: read G4C_EDGE_MODE on first use
-
-void edge_pair_set_mode(int mode) { g_edge_mode = mode; }
-
-int edge_pair_mode() {
-    if (g_edge_mode < 0) {
-        const char* e = std::getenv("G4C_EDGE_MODE");
-        g_edge_mode = e ? std::atoi(e) : 0;
-        if (g_edge_mode < 0 || g_edge_mode > 4) g_edge_mode = 0;
-    }
-    return g_edge_mode;
-}
-
-bool edge_pair_tma_supported(const EdgeArgs& a) {
+bool edge_v5_supported(const EdgeArgs& a) {
     return a.fixed_k > 0 && a.edge_perm == nullptr && a.tgt_perm == nullptr && a.n_targets > 0;
 }
 
-int edge_pair_tma_launch(const EdgeArgs& a, int mode, cudaStream_t st) {
-    if (!edge_pair_tma_supported(a)) { set_error("edge_pair_tma_launch: needs fixed_k > 0 and no permutations"); return G4C_EUNSUPPORTED; }
+int edge_v5_launch(const EdgeArgs& a, cudaStream_t st) {
+    if (!edge_v5_supported(a)) { set_error("edge_v5_launch: needs fixed_k > 0 and no permutations"); return G4C_EUNSUPPORTED; }
     if (a.act_e_out != G4C_ACT_NONE && a.act_e_out != G4C_ACT_SELU) { set_error("g4c_edge_aggr_fwd: act_e_out must be none or selu"); return G4C_EUNSUPPORTED; }
-    ep4::Maps tm;
-    bool ok = ep4::encode(&tm.e_in, a.e_in, a.n_targets, a.fixed_k, 16, CU_TENSOR_MAP_SWIZZLE_64B) &&
-              ep4::encode(&tm.p_c, a.P_c, a.n_targets, 0, 16, CU_TENSOR_MAP_SWIZZLE_64B) &&
-              ep4::encode(&tm.e_out, a.e_out ? a.e_out : a.e_in, a.n_targets, a.fixed_k, 8, CU_TENSOR_MAP_SWIZZLE_32B) &&
-              // tile::gather4 map: one-row box, four row coordinates per copy.  The descriptor does not carry the number of source
-              // rows (G4cEdgeDesc has no such field); the bound only matters for out-of-range coordinates, which are never issued.
-              ep4::encode(&tm.p_r, a.P_r, (int64_t)1 << 28, 0, 16, CU_TENSOR_MAP_SWIZZLE_64B, 1);
-    if (!ok) { set_error("edge_pair_tma_launch: cuTensorMapEncodeTiled failed"); return G4C_ECUDA; }
-    static bool configured = false;
-    const int smem = (int)sizeof(ep4::Smem);
-    if (!configured) {
-        if (cudaFuncSetAttribute(ep4::edge_tma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
-            cudaFuncSetAttribute(ep4::edge_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
-            cudaFuncSetAttribute(ep4::edge_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
-            cudaFuncSetAttribute(ep4::edge_tma_kernel<2, 96, 48>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
-            return check_launch("edge_tma_kernel attribute");
-        configured = true;
-    }
-    static int n_sm = 0;
-    if (n_sm == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        if (n_sm <= 0) n_sm = 148;
-    }
+    ep5::Maps tm;
+    const bool ok = ep5::encode_rows(&tm.e_in, a.e_in, a.n_targets, a.fixed_k, 16, 64, 32) &&
+                    ep5::encode_rows(&tm.p_c, a.P_c, a.n_targets, 0, 16, 64, 32) &&
+                    ep5::encode_rows(&tm.e_out, a.e_out ? a.e_out : a.e_in, a.n_targets, a.fixed_k, 8, 32, 32);
+    if (!ok) { set_error("edge_v5_launch: cuTensorMapEncodeTiled failed"); return G4C_ECUDA; }
+    static int configured[kMaxDevices] = {0};
+    const int smem = (int)sizeof(ep5::Smem);
+    if (!ensure_dynamic_smem(ep5::edge_v5_kernel, smem, configured)) return check_launch("edge_v5_kernel attribute");
+    const int n_sm = device_sms();
     const int64_t n_units = (a.n_targets + 127) / 128, n_up = (n_units + 1) / 2;
     const int pairs = (int)std::min<int64_t>(n_up, n_sm / 2);
-    if (mode >= 4) ep4::edge_tma_kernel<2, 96, 48><<<2 * pairs, ep4::NT, smem, st>>>(a, tm);
-    else if (mode == 3) ep4::edge_tma_kernel<2><<<2 * pairs, ep4::NT, smem, st>>>(a, tm);
-    else if (mode == 2) ep4::edge_tma_kernel<1><<<2 * pairs, ep4::NT, smem, st>>>(a, tm);
-    else ep4::edge_tma_kernel<0><<<2 * pairs, ep4::NT, smem, st>>>(a, tm);
+    ep5::edge_v5_kernel<<<2 * pairs, ep5::NT, smem, st>>>(a, tm);
     count_launch();
-    return check_launch("edge_tma_kernel");
+    return check_launch("edge_v5_kernel");
 }
 
 }  // namespace g4c

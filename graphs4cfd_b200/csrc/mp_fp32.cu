@@ -229,27 +229,14 @@ static size_t rowmlp_smem_bytes() {
     return (size_t)(2 * C::TM * C::LD + C::TM * C::SMALL_LD + C::WST) * sizeof(float) + C::TM * sizeof(int);
 }
 
-static int num_sms() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
-    }
-    return n;
-}
+static int num_sms() { return device_sms(); }
 
 template <int H>
 static int launch_mp(const G4cMpDesc& d, cudaStream_t st) {
     using C = Cfg<H>;
-    static bool configured = false;
+    static int configured[kMaxDevices] = {0};
     const size_t smem = mp_smem_bytes<H>();
-    if (!configured) {
-        if (cudaFuncSetAttribute(mp_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return check_launch("mp_kernel attribute");
-        configured = true;
-    }
+    if (!ensure_dynamic_smem(mp_kernel<H>, (int)smem, configured)) return check_launch("mp_kernel attribute");
     const int64_t n_units = (d.n_targets + C::TM - 1) / C::TM;
     const int per_sm = (H <= 128) ? 2 : 1;
     const int grid = (int)std::min<int64_t>(n_units, (int64_t)num_sms() * per_sm);
@@ -261,13 +248,9 @@ static int launch_mp(const G4cMpDesc& d, cudaStream_t st) {
 template <int H>
 static int launch_rowmlp(const G4cRowMlpDesc& d, cudaStream_t st) {
     using C = Cfg<H>;
-    static bool configured = false;
+    static int configured[kMaxDevices] = {0};
     const size_t smem = rowmlp_smem_bytes<H>();
-    if (!configured) {
-        if (cudaFuncSetAttribute(rowmlp_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return check_launch("rowmlp_kernel attribute");
-        configured = true;
-    }
+    if (!ensure_dynamic_smem(rowmlp_kernel<H>, (int)smem, configured)) return check_launch("rowmlp_kernel attribute");
     const int64_t n_tiles = (d.rows + C::TM - 1) / C::TM;
     const int per_sm = (H <= 128) ? 2 : 1;
     const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)num_sms() * per_sm);

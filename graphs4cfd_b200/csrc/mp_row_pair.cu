@@ -469,19 +469,9 @@ int row_pair_launch(const G4cRowTcDesc& d, cudaStream_t st) {
     if (smem > pairk::kMaxSmem) { set_error("g4c_rowmlp_tc_fwd: weights (%u bytes per CTA) leave no room for the input rings", off); return G4C_EUNSUPPORTED; }
     const int64_t n_pt = (d.rows + 255) / 256;
     a.n_pt = n_pt;
-    static int configured_smem = 0;
-    if (smem > configured_smem) {
-        if (cudaFuncSetAttribute(rp::row_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
-            return check_launch("row_pair_kernel attribute");
-        configured_smem = smem;
-    }
-    static int n_sm = 0;
-    if (n_sm == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        if (n_sm <= 0) n_sm = 148;
-    }
+    static int configured[kMaxDevices] = {0};
+    if (!ensure_dynamic_smem(rp::row_pair_kernel, smem, configured)) return check_launch("row_pair_kernel attribute");
+    const int n_sm = device_sms();
     const int pairs = (int)std::min<int64_t>(n_pt, n_sm / 2);
     rp::row_pair_kernel<<<2 * pairs, pairk::NT, smem, st>>>(a);
     count_launch();

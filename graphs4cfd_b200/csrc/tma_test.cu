@@ -1,24 +1,23 @@
-// tma_test.cu — hardware self tests of the bulk-tensor (TMA) assumptions mp_edge_pair_tma.cu is built on, one warp each:
+// tma_test.cu — hardware self tests of the bulk-tensor (TMA) assumptions mp_edge_v5.cu is built on, one warp each:
 //   test 0  3-D tile load, box 16 x 1 x 32 of the [rows, k, 128] view, SWIZZLE_64B: where the bytes land in shared memory
 //           (read back with the loader's lane = row formula)
 //   test 1  3-D tile store, box 8 x 1 x 32, SWIZZLE_32B, from a tile staged with the epilogue's formula
-//   test 2  tile::gather4 load (one-row box, four row coordinates per copy, eight copies by lanes 0-7 with divergent operands)
 //   test 3  test 0 with the tile hanging over the end of the tensor: out-of-bounds rows are zero-filled and still count
 //           towards the mbarrier's transaction bytes
-// EXPERIMENTAL like the kernel they support (tests/test_gpu_tma_primitives.py, opt-in): not yet run on hardware.
+// (tests/test_gpu_tma_primitives.py)
 #include <cuda.h>
 #include "tc2_core.cuh"
 #include "mp_pair.h"
 
 namespace g4c {
-namespace ep4 {
+namespace ep5 {
 bool encode_rows(CUtensorMap* m, const float* base, int64_t rows, int k, int box_cols, int swizzle_bytes, int box_rows);
 }
 namespace tmat {
 
 using namespace tc2;
 
-struct Maps { CUtensorMap in3, out3, in2; };
+struct Maps { CUtensorMap in3, out3; };
 
 __device__ __forceinline__ void wait_bar(uint32_t bar, uint32_t parity) {
     uint32_t ok, spins = 0;
@@ -30,7 +29,7 @@ __device__ __forceinline__ void wait_bar(uint32_t bar, uint32_t parity) {
 }
 
 // c0, j, n0: tile origin (column, in-edge slot, first target row)
-__global__ void __launch_bounds__(32, 1) tma_test_kernel(int test, const __grid_constant__ Maps tm, const float* src, const int32_t* idx,
+__global__ void __launch_bounds__(32, 1) tma_test_kernel(int test, const __grid_constant__ Maps tm, const float* src,
                                                           float* out, int c0, int j, int n0) {
     __shared__ __align__(1024) uint8_t tile[2048];
     __shared__ uint64_t bar;
@@ -45,18 +44,8 @@ __global__ void __launch_bounds__(32, 1) tma_test_kernel(int test, const __grid_
                          ::"r"(t), "l"(&tm.in3), "r"(c0), "r"(j), "r"(n0), "r"(b) : "memory");
         }
         wait_bar(b, 0);
-    } else if (test == 2) {
-        int r[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) r[i] = idx[(4 * lane + i) & 31];
-        if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(2048) : "memory");
-        __syncwarp();
-        if (lane < 8)
-            asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
-                         ::"r"(t + 256u * lane), "l"(&tm.in2), "r"(c0), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(b) : "memory");
-        wait_bar(b, 0);
     }
-    if (test == 0 || test == 2 || test == 3) {
+    if (test == 0 || test == 3) {
         // the loader's read-back: lane = row, 64-byte pitch, 16-byte chunk c at c ^ ((lane >> 1) & 3)
         const uint32_t swz = (uint32_t)((lane >> 1) & 3);
 #pragma unroll
@@ -84,15 +73,12 @@ __global__ void __launch_bounds__(32, 1) tma_test_kernel(int test, const __grid_
 
 }  // namespace tmat
 
-// src: [rows * k, 128] (tests 0, 1, 3) or [rows, 128] (test 2); out: [32, 16] (tests 0, 2, 3) or [rows * k, 128] (test 1)
-int tma_test_launch(int test, const float* src, int64_t rows, int k, const int32_t* idx, float* out, int c0, int j, int n0, cudaStream_t st) {
+// src: [rows * k, 128]; out: [32, 16] (tests 0, 3) or [rows * k, 128] (test 1)
+int tma_test_launch(int test, const float* src, int64_t rows, int k, float* out, int c0, int j, int n0, cudaStream_t st) {
     tmat::Maps tm;
-    // every test uses one of the three maps; the other two are encoded on the same memory and never referenced
-    bool ok = ep4::encode_rows(&tm.in3, src, test == 2 ? 1 : rows, test == 2 ? 1 : k, 16, 64, 32) &&
-              ep4::encode_rows(&tm.out3, test == 1 ? out : src, test == 2 ? 1 : rows, test == 2 ? 1 : k, 8, 32, 32) &&
-              ep4::encode_rows(&tm.in2, src, test == 2 ? rows : rows * (int64_t)k, 0, 16, 64, 1);
+    const bool ok = ep5::encode_rows(&tm.in3, src, rows, k, 16, 64, 32) && ep5::encode_rows(&tm.out3, test == 1 ? out : src, rows, k, 8, 32, 32);
     if (!ok) { set_error("g4c_debug_tma: cuTensorMapEncodeTiled failed"); return G4C_ECUDA; }
-    tmat::tma_test_kernel<<<1, 32, 0, st>>>(test, tm, src, idx, out, c0, j, n0);
+    tmat::tma_test_kernel<<<1, 32, 0, st>>>(test, tm, src, out, c0, j, n0);
     count_launch();
     return check_launch("tma_test_kernel");
 }

@@ -9,33 +9,6 @@ import torch
 from . import _lib as L
 
 
-def pack_weight_fp16x2(W: torch.Tensor):
-    """Tensor-core operand image of one nn.Linear weight W [128, K] (torch layout, K % 64 == 0):
-    s*W = hi + lo in fp16 (s a power of two keeping |s*W| in [512, 1024) so the residual stays a normal
-    fp16), each 64-wide K-block stored as a 128-row x 128-byte SWIZZLE_128B K-major image, hi image then
-    lo image (32 KiB per K-block).  Returns (uint8 tensor, 1/s)."""
-    N, K = W.shape
-    assert N == 128 and K % 64 == 0, "tensor-core path: weights must be [128, 64*j]"
-    W = W.detach().float()
-    amax = float(W.abs().max())
-    s = 1.0 if amax == 0.0 else 2.0 ** min(14, math.floor(math.log2(1000.0 / amax)))
-    Ws = W * s
-    hi = Ws.half()
-    lo = (Ws - hi.float()).half()
-    r = torch.arange(128, device=W.device)
-    c = torch.arange(8, device=W.device)
-    phys = c.unsqueeze(0) ^ (r.unsqueeze(1) & 7)                       # [128, 8]: position of logical chunk c in row r
-
-    def image(M):
-        blk = M.view(128, K // 64, 8, 8).permute(1, 0, 2, 3)            # [kb, row, chunk, 8]
-        out = torch.empty_like(blk)
-        out[:, r.unsqueeze(1), phys, :] = blk
-        return out.reshape(K // 64, 1, 128, 64)
-
-    pack = torch.cat([image(hi), image(lo)], dim=1).contiguous()        # [kb, hi|lo, 128, 64] fp16
-    return pack.view(torch.uint8).reshape(-1), 1.0 / s
-
-
 def _swizzled_images(M: torch.Tensor):
     """fp16 [R, K] (R % 8 == 0, K % 64 == 0) -> [K/64, R, 64] fp16, each a SWIZZLE_128B K-major image."""
     R, K = M.shape
@@ -100,7 +73,6 @@ class MlpPack:
                                            ln[1].detach().float().contiguous().clone())
         L.require_cuda_f32(*self.W_t, *self.b)
         self._struct = None
-        self.W_pack, self.w_inv_scale = [], []      # (first-generation single-CTA images: no longer produced)
 
     # ---- tensor-core (fp16x3, CTA-pair kernels) operand images, built on first use
     def tc_row_ok(self, seg_widths) -> bool:
@@ -123,7 +95,10 @@ class MlpPack:
         if self._tc_edge is None:
             ep = EdgePairPack(self._linears, self._ln_raw)
             zero = torch.zeros_like(ep.b1)
-            self._tc_edge = (ep, RowPairPack([(ep.W1s, zero)], [128]), RowPairPack([(ep.W1t, ep.b1)], [128]))
+            # P_r, P_c leave the row kernel already multiplied by the layer-1 scale s (a power of two: exact), so the
+            # edge kernel's loaders only add them (G4cEdgeDesc.p_scale = 1)
+            self._tc_edge = (ep, RowPairPack([(ep.W1s, zero)], [128], out_scale=ep.p_scale),
+                             RowPairPack([(ep.W1t, ep.b1)], [128], out_scale=ep.p_scale))
         return self._tc_edge
 
     @classmethod
@@ -157,9 +132,6 @@ class MlpPack:
                 m.b[i] = self.b[i].data_ptr()
             if self.ln is not None:
                 m.ln_gamma, m.ln_beta = self.ln[0].data_ptr(), self.ln[1].data_ptr()
-            for i, pk in enumerate(self.W_pack):
-                m.W_pack[i] = pk.data_ptr()
-                m.w_inv_scale[i] = self.w_inv_scale[i]
             self._struct = m
         return self._struct
 
@@ -201,8 +173,11 @@ class RowPairPack:
     for g4c_rowmlp_tc_fwd.  ``seg_widths`` are the widths of the concatenated input segments in order (each 128
     or <= 16): linear_1's columns are re-laid out K-block by K-block (narrow segments zero-padded to 64)."""
 
-    def __init__(self, linears: Sequence[Tuple[torch.Tensor, torch.Tensor]], seg_widths: Sequence[int], ln=None):
+    def __init__(self, linears: Sequence[Tuple[torch.Tensor, torch.Tensor]], seg_widths: Sequence[int], ln=None,
+                 out_scale: float = 1.0):
         assert 1 <= len(linears) <= 3
+        assert out_scale == 1.0 or (len(linears) == 1 and ln is None), "out_scale: bare Linear only"
+        self.out_scale = float(out_scale)
         dev = linears[0][0].device
         W1 = linears[0][0].detach().float()
         assert W1.shape[0] == 128 and W1.shape[1] == sum(seg_widths), "hidden width 128 and matching input width"
@@ -229,8 +204,8 @@ class RowPairPack:
                 assert W.shape[0] == 128
             pk, inv = pack_weight_pair(W.contiguous())
             self.W_pair.append(pk)
-            self.inv_scale.append(inv)
-            self.bias.append(b.contiguous().clone())
+            self.inv_scale.append(inv * self.out_scale)           # out = out_scale * (x W^T + b)
+            self.bias.append((b * self.out_scale).contiguous().clone())
         self.ln = None if ln is None else (ln[0].detach().float().contiguous().clone(),
                                            ln[1].detach().float().contiguous().clone())
 
@@ -282,9 +257,14 @@ def dual_linear_tc(pack_a: RowPairPack, pack_b: RowPairPack, x: torch.Tensor, ou
     return out_a, out_b
 
 
+EDGE_VARIANTS = {"auto": L.EDGE_AUTO, "v3": L.EDGE_V3, "v5": L.EDGE_V5}
+EDGE_VARIANT_DEFAULT = "auto"       # benchmarks may pin a kernel for every launch of the process (bench.py --edge-variant)
+
+
 def edge_aggr(pack: EdgePairPack, topo: "MpTopo", e_in, P_r, P_c, aggr="mean", act_e=None, want_e=True,
-              e_out=None, agg_out=None):
-    """g4c_edge_aggr_fwd: returns (agg [n_targets,128], e_out|None)."""
+              e_out=None, agg_out=None, p_prescaled=False, variant=None):
+    """g4c_edge_aggr_fwd: returns (agg [n_targets,128], e_out|None).  ``p_prescaled``: P_r / P_c already carry the
+    layer-1 scale (MlpPack.tc_edge's projections do); ``variant`` pins a kernel (tests, tools/bench_edge.py)."""
     L.require_cuda_f32(e_in, P_r, P_c)
     d = L.EdgeDesc()
     d.n_targets, d.n_edges, d.fixed_k, d.n_layers = topo.n_targets, topo.n_edges, topo.fixed_k, pack.n_layers
@@ -303,7 +283,8 @@ def edge_aggr(pack: EdgePairPack, topo: "MpTopo", e_in, P_r, P_c, aggr="mean", a
         d.W[i] = pack.W_pair[i].data_ptr()
         d.inv_scale[i] = pack.inv_scale[i]
         d.bias[i] = pack.bias[i].data_ptr()
-    d.p_scale = pack.p_scale
+    d.p_scale = 1.0 if p_prescaled else pack.p_scale
+    d.variant = EDGE_VARIANTS[EDGE_VARIANT_DEFAULT if variant is None else variant]
     if pack.ln is not None:
         d.gamma, d.beta = pack.ln[0].data_ptr(), pack.ln[1].data_ptr()
     L.check(L.lib().g4c_edge_aggr_fwd(C.byref(d), L.stream_ptr()))
@@ -408,7 +389,8 @@ def mp(edge_pack: MlpPack, node_pack: MlpPack, topo: MpTopo, e_in, src_feat, tgt
             P_c = rowmlp_tc(proj_t, [(tgt_feat, None, 1.0)], out=P_c)
         if agg is None:
             agg = torch.empty(tgt_feat.shape[0], 128, device=dev, dtype=torch.float32)
-        agg, e_out = edge_aggr(ep, topo, e_in, P_r, P_c, aggr=aggr, act_e=act_e, want_e=want_e, e_out=e_out, agg_out=agg)
+        agg, e_out = edge_aggr(ep, topo, e_in, P_r, P_c, aggr=aggr, act_e=act_e, want_e=want_e, e_out=e_out, agg_out=agg,
+                                p_prescaled=True)
         t_out = rowmlp_tc(node_pack.tc_row([128, 128]), [(agg, None, 1.0), (tgt_feat, None, 1.0)], act=act_t, out=t_out)
         return t_out, e_out
     d = L.MpDesc()
@@ -510,20 +492,25 @@ def halo_unpack(buf, idx, dst):
     return dst
 
 
+def _pack_weight_single(W: torch.Tensor):
+    """Single-CTA operand image of W [128, K] for the self tests 1 / 2 of csrc/tc2_test.cu: per 64-wide K-block the
+    128-row hi image then the lo image (SWIZZLE_128B K-major).  Returns (uint8 tensor, 1/s)."""
+    N, K = W.shape
+    assert N == 128 and K % 64 == 0
+    W = W.detach().float()
+    s = weight_scale(W)
+    Ws = W * s
+    hi = Ws.half()
+    lo = (Ws - hi.float()).half()
+    pack = torch.stack([_swizzled_images(hi), _swizzled_images(lo)], dim=1).contiguous()        # [kb, hi|lo, 128, 64]
+    return pack.view(torch.uint8).reshape(-1), 1.0 / s
+
+
 def debug_tc2(test: int, A: torch.Tensor, W: torch.Tensor, P: Optional[torch.Tensor] = None, flags: int = 0) -> torch.Tensor:
     """Self tests of the TMEM-operand / tcgen05.cp / CTA-pair primitives (csrc/tc2_test.cu)."""
     L.require_cuda_f32(A, W, P)
-    pk, inv = pack_weight_pair(W) if test == 3 else pack_weight_fp16x2(W)
+    pk, inv = pack_weight_pair(W) if test == 3 else _pack_weight_single(W)
     D = torch.zeros(A.shape[0], 128, device=A.device, dtype=torch.float32)
     L.check(L.lib().g4c_debug_tc2(test, A.data_ptr(), pk.data_ptr(), inv, 0 if P is None else P.data_ptr(),
                                   D.data_ptr(), flags, L.stream_ptr()))
-    return D
-
-
-def debug_tc_gemm(A: torch.Tensor, W: torch.Tensor) -> torch.Tensor:
-    """A[128,K] @ W[128,K]^T through the tensor-core GEMM core (self test)."""
-    L.require_cuda_f32(A, W)
-    pk, inv = pack_weight_fp16x2(W)
-    D = torch.empty(128, 128, device=A.device, dtype=torch.float32)
-    L.check(L.lib().g4c_debug_tc_gemm(A.data_ptr(), pk.data_ptr(), inv, int(A.shape[1]), D.data_ptr(), L.stream_ptr()))
     return D

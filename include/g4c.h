@@ -37,8 +37,11 @@ enum { G4C_ACT_NONE = 0, G4C_ACT_SELU = 1, G4C_ACT_TANH = 2 };
 enum { G4C_AGGR_MEAN = 0, G4C_AGGR_SUM = 1 };
 /* arithmetic of the dense layers */
 enum { G4C_PREC_FP32 = 0,     /* fp32 FFMA on CUDA cores: exact-fp32 parity path            */
-       G4C_PREC_FP16X3 = 1,   /* tcgen05 tensor cores, operands split hi+lo fp16, 3 MMAs    */
-       G4C_PREC_BF16 = 2 };   /* tcgen05 single pass bf16 (fast, NOT within parity tolerance) */
+       G4C_PREC_FP16X3 = 1 }; /* tcgen05 tensor cores, operands split hi+lo fp16, 3 MMAs    */
+/* kernel behind g4c_edge_aggr_fwd */
+enum { G4C_EDGE_AUTO = 0,     /* v5 when the launch has a fixed in-degree and no permutations, v3 otherwise */
+       G4C_EDGE_V3 = 1,       /* csrc/mp_edge_pair.cu: cp.async loaders, any topology        */
+       G4C_EDGE_V5 = 2 };     /* csrc/mp_edge_v5.cu: TMA tiles, packed fp32 epilogues        */
 
 #define G4C_MAX_LAYERS 3
 #define G4C_MAX_SEGS 3
@@ -54,13 +57,6 @@ typedef struct {
     const float* b[G4C_MAX_LAYERS];
     const float* ln_gamma;            /* NULL = no layer_norm                                 */
     const float* ln_beta;
-    /* tensor-core operand images (G4C_PREC_FP16X3), NULL when only the fp32 path is used:
-     * layer l = in_l/64 stages of 32 KiB; stage kb = fp16(s*W)[:, 64kb:64kb+64] as a 128-row x 128 B
-     * SWIZZLE_128B K-major image (16 KiB) followed by the same image of the residual
-     * fp16(s*W - hi) (16 KiB); w_inv_scale[l] = 1/s, s a power of two. */
-    const void* W_pack[G4C_MAX_LAYERS];
-    float w_inv_scale[G4C_MAX_LAYERS];
-    int32_t _pad;
 } G4cMlp;
 
 /* One input segment of a concatenation `torch.cat((seg0, seg1, ...), dim=-1)`. */
@@ -211,7 +207,8 @@ typedef struct {
  *     agg[t] = mean|sum over the in-edges of t of e'           (blocks.py:183, 330, 378)
  * Topology fields have the meaning they have in G4cMpDesc.  Weights are "pair images" (ops.pack_weight_pair:
  * fp16 hi/lo split of s*W, 64 output rows per CTA, SWIZZLE_128B K-major); W_pair[0] holds the e-columns of
- * linear_1 and must share the scale s of P (p_scale = s). */
+ * linear_1 with scale s; the kernel adds p_scale * (P_r[src] + P_c[tgt]) to s * W1e e, so either pass the plain
+ * products with p_scale = s, or products already multiplied by s (an exact power of two) with p_scale = 1. */
 typedef struct {
     int64_t n_targets, n_edges;
     int32_t fixed_k, n_layers, act_e_out, aggr;
@@ -230,6 +227,8 @@ typedef struct {
     const float* bias[3];             /* bias[0] unused (folded into P_c)                      */
     const float* gamma;               /* LayerNorm affine or NULL                              */
     const float* beta;
+    int32_t variant;                  /* G4C_EDGE_AUTO (0) unless a test / benchmark pins a kernel */
+    int32_t _pad;
 } G4cEdgeDesc;
 
 /* Row-tile MLP on the tensor cores (hidden = 128, precision fp16x3), CTA-pair kernel (csrc/mp_row_pair.cu):
@@ -284,32 +283,23 @@ G4C_API int g4c_halo_unpack(const G4cHaloDesc* d, void* stream);
 /* number of kernels this library has launched since load (bench.py reports it as gpu_launches) */
 G4C_API int64_t g4c_launch_count(void);
 
-/* host-side plan helper (HOST pointers): Guillard node-nested coarsening, the sequential sweep of
- * transforms/mugs.py:8-29.  senders = int64 [n, k]; coarse_mask = uint8 [n] (out). */
-/* self-test of the tensor-core GEMM core: D[128,128] = A[128,K] * W^T with the 3-term fp16 split,
- * W given as a W_pack image (K % 64 == 0, K <= 128).  Used by tests/test_gpu_tc.py. */
-G4C_API int g4c_debug_tc_gemm(const float* A, const void* W_pack, float w_inv_scale, int32_t K, float* D, void* stream);
-
 /* self tests of the second-generation primitives (A operand in TMEM, tcgen05.cp, CTA pairs); see
  * graphs4cfd_b200/csrc/tc2_test.cu for the meaning of test / flags.  Used by tests/test_gpu_tc2.py. */
 G4C_API int g4c_debug_tc2(int32_t test, const float* A, const void* W_pack, float w_inv_scale, const float* P, float* D,
                           int32_t flags, void* stream);
 
-/* in-kernel phase profile of edge_pair_kernel (HOST pointer to 64 uint64; only in builds with -DG4C_PROFILE) */
-G4C_API int g4c_debug_profile(uint64_t* out64);
+/* in-kernel phase profile of the edge kernel `variant` (G4C_EDGE_V3 / G4C_EDGE_V5; HOST pointer to 64 uint64; only in
+ * builds with -DG4C_PROFILE) */
+G4C_API int g4c_debug_profile(int32_t variant, uint64_t* out64);
 
-/* EXPERIMENTAL: variant of the kernel behind g4c_edge_aggr_fwd for launches with fixed_k > 0 and no permutations
- * (csrc/mp_edge_pair_tma.cu).  0 = default kernel; 1 = e' staged in shared memory and written by TMA tensor stores;
- * 2 = 1 + e / P_c tiles read by TMA tensor loads; 3 = 2 + the gathered P_r rows read by TMA gather4; 4 = 3 with another register split.  Same result as mode 0.  The environment variable
- * G4C_EDGE_MODE sets the initial value. */
-G4C_API int g4c_debug_set_edge_mode(int32_t mode);
+/* one-warp hardware self tests of the bulk-tensor (TMA) copies csrc/mp_edge_v5.cu relies on (csrc/tma_test.cu):
+ * 0 = 3-D tile load, 1 = 3-D tile store, 3 = tile load hanging over the end of the tensor.
+ * src = [rows * k, 128] fp32; out = [32, 16] (test 1: [rows * k, 128]); tile origin (c0, j, n0). */
+G4C_API int g4c_debug_tma(int32_t test, const float* src, int64_t rows, int32_t k, float* out, int32_t c0, int32_t j, int32_t n0,
+                          void* stream);
 
-/* EXPERIMENTAL: one-warp hardware self tests of the bulk-tensor (TMA) copies the variants above rely on (csrc/tma_test.cu):
- * 0 = 3-D tile load, 1 = 3-D tile store, 2 = gather4 load, 3 = tile load hanging over the end of the tensor.
- * src = [rows * k, 128] fp32 (test 2: [rows, 128]); out = [32, 16] (test 1: [rows * k, 128]); tile origin (c0, j, n0). */
-G4C_API int g4c_debug_tma(int32_t test, const float* src, int64_t rows, int32_t k, const int32_t* idx, float* out,
-                          int32_t c0, int32_t j, int32_t n0, void* stream);
-
+/* host-side plan helper (HOST pointers): Guillard node-nested coarsening, the sequential sweep of
+ * transforms/mugs.py:8-29.  senders = int64 [n, k]; coarse_mask = uint8 [n] (out). */
 G4C_API int g4c_host_guillard(const int64_t* senders, int64_t n, int32_t k, uint8_t* coarse_mask);
 
 #ifdef __cplusplus

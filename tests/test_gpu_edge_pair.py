@@ -95,25 +95,14 @@ def test_edge_pair_discarded_edge_output():
     _run(n, row, col, 3, "mean", "selu", want_e=False)
 
 
-# ---- experimental bulk-tensor (TMA) variants of the kernel (csrc/mp_edge_pair_tma.cu).  They were written after the
-# round's GPU budget was spent and have not run on hardware yet, so they are opt-in:  G4C_TEST_EXPERIMENTAL=1 pytest -m gpu ...
-experimental = pytest.mark.skipif(__import__("os").environ.get("G4C_TEST_EXPERIMENTAL") != "1",
-                                  reason="experimental kernel variants: set G4C_TEST_EXPERIMENTAL=1")
-
-
-def _set_mode(mode):
-    ops.L.check(ops.L.lib().g4c_debug_set_edge_mode(mode))
-
-
 @gpu
-@experimental
-@pytest.mark.parametrize("mode", [1, 2, 3, 4], ids=["mode1", "mode2", "mode3", "mode4"])
-@pytest.mark.parametrize("n,k", [(1000, 6), (256, 5), (77, 6), (40000, 6), (128, 1), (129, 2)])
+@pytest.mark.parametrize("variant", ["v3", "v5"])
+@pytest.mark.parametrize("n,k", [(1000, 6), (256, 5), (77, 6), (40000, 6), (128, 1), (129, 2), (300, 7)])
 @pytest.mark.parametrize("n_layers", [3, 2])
 @pytest.mark.parametrize("want_e", [True, False])
-def test_edge_pair_tma_modes_match_default(mode, n, k, n_layers, want_e):
-    """Modes 1 .. 4 move the same values through different data paths: results must equal mode 0 bit for bit, and the fp64
-    restatement within the kernel's tolerance."""
+def test_edge_pair_variants_fixed_k(variant, n, k, n_layers, want_e):
+    """Both kernels behind g4c_edge_aggr_fwd on fixed in-degree launches (v5 = the default there; v3 = the kernel for CSR /
+    permuted launches, pinned here): each against the fp64 restatement, tail units, odd k, discarded e', act none / selu."""
     dev = torch.device("cuda")
     g = torch.Generator().manual_seed(n + k)
     col = torch.arange(n).repeat_interleave(k).to(dev)
@@ -127,17 +116,31 @@ def test_edge_pair_tma_modes_match_default(mode, n, k, n_layers, want_e):
     P_c = (v.double() @ pack.W1t.double().t() + pack.b1.double()).float().contiguous()
     topo = ops.MpTopo.from_edge_index(torch.stack([row, col]), n)
     assert topo.fixed_k == k and topo.edge_perm is None
-    try:
-        _set_mode(0)
-        agg0, e0 = ops.edge_aggr(pack, topo, e, P_r, P_c, aggr="mean", act_e="selu", want_e=want_e)
+    for act in ("selu", None):
+        e_ref, agg_ref = _ref(lin, ln, e, v, row, col, n, "mean", act)
+        agg1, e1 = ops.edge_aggr(pack, topo, e, P_r, P_c, aggr="mean", act_e=act, want_e=want_e, variant=variant)
         torch.cuda.synchronize()
-        _set_mode(mode)
-        agg1, e1 = ops.edge_aggr(pack, topo, e, P_r, P_c, aggr="mean", act_e="selu", want_e=want_e)
-        torch.cuda.synchronize()
-    finally:
-        _set_mode(0)
-    assert torch.equal(agg0, agg1)
-    if want_e:
-        assert torch.equal(e0, e1)
-    e_ref, agg_ref = _ref(lin, ln, e, v, row, col, n, "mean", "selu")
-    assert float((agg1.double() - agg_ref).norm() / agg_ref.norm()) < 2e-5
+        assert float((agg1.double() - agg_ref).norm() / agg_ref.norm()) < 2e-5
+        if want_e:
+            assert float((e1.double() - e_ref).norm() / e_ref.norm()) < 2e-5
+            assert float((e1.double() - e_ref).abs().max()) < 1e-4
+    # products already multiplied by the layer-1 scale (what the row kernel hands over inside a block)
+    agg2, _ = ops.edge_aggr(pack, topo, e, P_r * pack.p_scale, P_c * pack.p_scale, aggr="sum", act_e="selu", want_e=want_e,
+                            p_prescaled=True, variant=variant)
+    _, agg_ref = _ref(lin, ln, e, v, row, col, n, "sum", "selu")
+    assert float((agg2.double() - agg_ref).norm() / agg_ref.norm()) < 2e-5
+
+
+@gpu
+def test_edge_pair_v5_rejects_irregular_launches():
+    dev = torch.device("cuda")
+    n = 300
+    col = torch.randint(0, n, (1500,), device=dev)
+    row = torch.randint(0, n, (1500,), device=dev)
+    lin, ln = _mlp(3, 1, dev)
+    pack = ops.EdgePairPack(lin, ln)
+    topo = ops.MpTopo.from_edge_index(torch.stack([row, col]), n)
+    assert topo.fixed_k == 0
+    P = torch.randn(n, 128, device=dev)
+    with pytest.raises(RuntimeError, match="fixed_k"):
+        ops.edge_aggr(pack, topo, torch.randn(1500, 128, device=dev), P, P, variant="v5")

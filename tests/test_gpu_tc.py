@@ -15,14 +15,16 @@ def dev(t):
     return t.cuda().contiguous()
 
 
-@pytest.mark.parametrize("K", [64, 128])
-def test_tc_gemm_core(K):
+@pytest.mark.parametrize("rows", [128, 1000])
+def test_tc_gemm_core(rows):
+    """The 3-term fp16 split GEMM on its own: a bare Linear through g4c_rowmlp_tc_fwd against fp64."""
     from graphs4cfd_b200 import ops
-    torch.manual_seed(K)
-    A = torch.randn(128, K) * 3.0
-    W = torch.randn(128, K) * 0.07
-    D = ops.debug_tc_gemm(dev(A), dev(W)).cpu()
-    ref = (A.double() @ W.double().t()).float()
+    torch.manual_seed(rows)
+    A = torch.randn(rows, 128) * 3.0
+    W = torch.randn(128, 128) * 0.07
+    b = torch.randn(128)
+    D = ops.rowmlp_tc(ops.RowPairPack([(dev(W), dev(b))], [128]), [(dev(A), None, 1.0)]).cpu()
+    ref = (A.double() @ W.double().t() + b.double()).float()
     assert rel_l2(D, ref) <= 2e-6, rel_l2(D, ref)
 
 

@@ -17,8 +17,8 @@ ap.add_argument("--spread", type=int, default=2000, help="sources are drawn with
 ap.add_argument("--layers", type=int, default=3)
 ap.add_argument("--no-e", action="store_true")
 ap.add_argument("--act", default="selu")
-ap.add_argument("--modes", default="0", help="comma-separated kernel variants to time (0 = default, 1 .. 4 = experimental TMA data paths, "
-                                            "csrc/mp_edge_pair_tma.cu); the outputs of every variant are compared with the first one's")
+ap.add_argument("--variants", default="v5", help="comma-separated kernels to time (v3 = csrc/mp_edge_pair.cu, v5 = csrc/mp_edge_v5.cu); "
+                                                "the outputs of every variant are compared with the first one's")
 a = ap.parse_args()
 
 dev = torch.device("cuda")
@@ -39,25 +39,25 @@ e_out = torch.empty_like(e)
 agg = torch.empty(n, 128, device=dev)
 
 
-def launch():
-    ops.edge_aggr(pack, topo, e, P_r, P_c, act_e=(None if a.act == "none" else a.act), want_e=not a.no_e, e_out=e_out, agg_out=agg)
+def launch(variant="auto"):
+    ops.edge_aggr(pack, topo, e, P_r, P_c, act_e=(None if a.act == "none" else a.act), want_e=not a.no_e, e_out=e_out, agg_out=agg,
+                  variant=variant)
 
 
 E = n * k
 alg = 4 * 128 * ((1 if a.no_e else 2) * E + 3 * n) + 4 * E
 flop = 2 * E * 128 * 128 * a.layers
 first = None
-for mode in [int(m) for m in a.modes.split(",")]:
-    ops.L.check(ops.L.lib().g4c_debug_set_edge_mode(mode))
+for variant in a.variants.split(","):
     e_out.fill_(float("nan"))
     agg.fill_(float("nan"))
     for _ in range(3):
-        launch()
+        launch(variant)
     torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(a.reps):
-        launch()
+        launch(variant)
     ev1.record()
     torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1) / a.reps
@@ -65,26 +65,24 @@ for mode in [int(m) for m in a.modes.split(",")]:
     if first is None:
         first = (agg.clone(), None if a.no_e else e_out.clone())
     else:
-        same = f"; agg equal to mode {a.modes.split(',')[0]}: {torch.equal(agg, first[0])}"
+        same = f"; vs {a.variants.split(',')[0]}: agg rel-L2 {float((agg - first[0]).norm() / first[0].norm()):.2e}"
         if not a.no_e:
-            same += f", e' equal: {torch.equal(e_out, first[1])}"
-    print(f"edge kernel mode {mode}: N={n} E={E} layers={a.layers} write_e={not a.no_e}: {ms:.3f} ms/launch, "
+            same += f", e' rel-L2 {float((e_out - first[1]).norm() / first[1].norm()):.2e}"
+    print(f"edge kernel {variant}: N={n} E={E} layers={a.layers} write_e={not a.no_e}: {ms:.3f} ms/launch, "
           f"{alg / ms / 1e6:.1f} GB/s algorithmic ({alg / 1e9:.2f} GB), {flop / ms / 1e9:.1f} TFLOP/s useful "
           f"({3 * flop / ms / 1e9:.1f} issued fp16){same}")
-ops.L.check(ops.L.lib().g4c_debug_set_edge_mode(0))
 
 if os.environ.get("G4C_PROFILE"):
     import ctypes as C
     import numpy as np
     from graphs4cfd_b200 import _lib as L
     buf = np.zeros(64, dtype=np.uint64)
-    prof_mode = int(a.modes.split(",")[-1])                          # the last variant of --modes is the one profiled
-    L.check(L.lib().g4c_debug_set_edge_mode(prof_mode))
-    L.lib().g4c_debug_profile(buf.ctypes.data_as(C.c_void_p))        # drop warm-up + timing launches
-    launch()
-    L.check(L.lib().g4c_debug_profile(buf.ctypes.data_as(C.c_void_p)))
-    L.check(L.lib().g4c_debug_set_edge_mode(0))
-    print(f"phase profile of mode {prof_mode} (the MMA issuer has no laps in the TMA variants):")
+    variant = a.variants.split(",")[-1]                              # the last variant is the one profiled
+    vcode = ops.EDGE_VARIANTS[variant]
+    L.lib().g4c_debug_profile(vcode, buf.ctypes.data_as(C.c_void_p))        # drop warm-up + timing launches
+    launch(variant)
+    L.check(L.lib().g4c_debug_profile(vcode, buf.ctypes.data_as(C.c_void_p)))
+    print(f"phase profile of {variant} (the MMA issuer has no laps in v5):")
     names = {0: ("epilogue warp 0", ["wait MMA (hidden)", "wait MMA (last)", "hidden epilogue", "last: statistics", "last: barrier", "last: normalise+agg+store", "unit end", "-"]),
              8: ("loader warp 16", ["wait rows", "wait acc release", "process + prefetch", "-", "-", "-", "-", "-"]),
              16: ("MMA issuer", ["wait loaders", "wait epilogue", "issue", "-", "-", "-", "-", "-"])}
@@ -92,5 +90,7 @@ if os.environ.get("G4C_PROFILE"):
     for base, (who, labels) in names.items():
         vals = buf[base:base + 8].astype(np.float64)
         tot = vals.sum()
+        if tot == 0:
+            continue
         print(f"{who}: total {tot / 1e6:.3f} Mcycles = {tot / n_slots:.0f} per slot; " +
               ", ".join(f"{l} {100 * v / tot:.1f}% ({v / n_slots:.0f}/slot)" for l, v in zip(labels, vals) if l != "-"))
