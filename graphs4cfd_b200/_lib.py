@@ -97,6 +97,7 @@ EXPORTS = {
     "g4c_version": (C.c_int, []),
     "g4c_last_error": (C.c_char_p, []),
     "g4c_launch_count": (C.c_int64, []),
+    "g4c_tc_launch_count": (C.c_int64, []),
     "g4c_rowmlp_fwd": (C.c_int, [C.POINTER(RowMlpDesc), C.c_void_p]),
     "g4c_mp_fwd": (C.c_int, [C.POINTER(MpDesc), C.c_void_p]),
     "g4c_rowmlp_tc_fwd": (C.c_int, [C.POINTER(RowTcDesc), C.c_void_p]),
@@ -142,12 +143,41 @@ def launch_count() -> int:
     return int(lib().g4c_launch_count())
 
 
+def tc_launch_count() -> int:
+    return int(lib().g4c_tc_launch_count())
+
+
 def ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
-def stream_ptr():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def stream_ptr(device=None):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def launch(name, desc, *tensors):
+    """Call the descriptor entry point ``name`` for tensors that must all live on ONE CUDA device: the kernel goes to that
+    device's current stream with that device made current for the call (kernel attributes, tensor maps and the launch
+    itself belong to the current device; PyTorch's current device is often a different one than the model's)."""
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError(f"graphs4cfd_b200 kernels need CUDA tensors (got device={t.device}); there is no CPU fallback")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"graphs4cfd_b200: tensors of one call live on different devices ({dev} and {t.device})")
+    if dev is None:
+        raise RuntimeError("graphs4cfd_b200: launch without a device tensor")
+    fn = getattr(lib(), name)
+    if dev.index == torch.cuda.current_device():
+        rc = fn(C.byref(desc), stream_ptr(dev))
+    else:
+        with torch.cuda.device(dev):
+            rc = fn(C.byref(desc), stream_ptr(dev))
+    check(rc)
 
 
 def require_cuda_f32(*tensors):

@@ -27,6 +27,18 @@ from ._lib import require_cuda_f32
 _DEFAULT_PRECISION = "auto"      # tensor cores (fp16x3) when hidden = 128, CUDA-core fp32 kernels otherwise
 
 
+def _row_precision(precision: str) -> str:
+    """Block precision -> ops.rowmlp precision: "fp16x3" engines take the tensor-core row kernel wherever it supports the
+    shape ("auto"), "fp32" engines never do."""
+    return "fp32" if precision == "fp32" else "auto"
+
+
+def _checked_static(t: torch.Tensor, what: str) -> torch.Tensor:
+    """Range check (ops.check_fp16_range) of a STATIC raw input, once per tensor (cached by identity: it synchronises)."""
+    _TOPO_CACHE.get(("range",) + _Cache.key(t), lambda: (ops.check_fp16_range(t, what), True)[1])
+    return t
+
+
 def _act_code(activation: Optional[Callable]):
     """Fold torch.tanh / F.selu into the kernel epilogue; anything else is applied afterwards."""
     if activation is None:
@@ -107,6 +119,7 @@ class MLP(nn.Module):
             layers["layer_norm"] = nn.LayerNorm(widths[-1])
         self.MLP = nn.Sequential(layers)
         self._pack, self._pack_key = None, None
+        self.precision = _DEFAULT_PRECISION
 
     @classmethod
     def adopt(cls, ref_mlp: nn.Module):
@@ -115,6 +128,7 @@ class MLP(nn.Module):
         nn.Module.__init__(self)
         self.MLP = ref_mlp.MLP
         self._pack, self._pack_key = None, None
+        self.precision = _DEFAULT_PRECISION
         return self
 
     def pack(self) -> ops.MlpPack:
@@ -126,7 +140,11 @@ class MLP(nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         require_cuda_f32(x)
         _no_grad_guard(x)
-        return ops.rowmlp(self.pack(), [(x, None, 1.0)])
+        # A stand-alone MLP fed by a narrow input is an encoder of RAW data (nn/mus_gnn.py:317-318, nn/remus_gnn.py:132-140):
+        # its range is the caller's, so "auto" keeps it on the exact-fp32 kernel (no fp16 operand split of unknown data).
+        raw = x.size(1) <= 16
+        prec = "fp32" if (self.precision == "fp32" or (self.precision == "auto" and raw)) else "auto"
+        return ops.rowmlp(self.pack(), [(x, None, 1.0)], precision=prec)
 
 
 class GNBlock(nn.Module):
@@ -186,6 +204,7 @@ class DownMP(nn.Module):
         self.down_mlp = MLP(*down_mlp_args)
         self.hr_graph_idx = hr_graph_idx
         self.lr_graph_idx = hr_graph_idx + 1
+        self.precision = _DEFAULT_PRECISION
 
     def forward(self, graph, activation: Optional[Callable] = None):
         h, l = self.hr_graph_idx, self.lr_graph_idx
@@ -194,7 +213,9 @@ class DownMP(nn.Module):
         require_cuda_f32(graph.field, graph.edge_attr, e_hl)
         _no_grad_guard(graph.field, graph.edge_attr)
         graph.pos = getattr(graph, f'pos_{l}')
-        x = ops.rowmlp(self.down_mlp.pack(), [(e_hl, None, 1.0), (graph.field, None, 1.0)])
+        if self.precision != "fp32":
+            _checked_static(e_hl, f"e_{h}{l}")
+        x = ops.rowmlp(self.down_mlp.pack(), [(e_hl, None, 1.0), (graph.field, None, 1.0)], precision=_row_precision(self.precision))
         n_l, cptr, cidx = _TOPO_CACHE.get(("children",) + _Cache.key(idx), lambda: children_csr(idx))
         code, post = _act_code(activation)
         graph.field = ops.seg_reduce(x, cptr, cidx, n_l, "mean", code)
@@ -218,6 +239,7 @@ class UpMP(nn.Module):
         self.up_mlp = MLP(*up_mlp_args)
         self.lr_graph_idx = lr_graph_idx
         self.hr_graph_idx = lr_graph_idx - 1
+        self.precision = _DEFAULT_PRECISION
 
     def forward(self, graph, field_hr_old: torch.Tensor, pos_hr: torch.Tensor, activation: Optional[Callable] = None):
         h, l = self.hr_graph_idx, self.lr_graph_idx
@@ -226,9 +248,11 @@ class UpMP(nn.Module):
         require_cuda_f32(graph.field, field_hr_old, e_hl)
         _no_grad_guard(graph.field, field_hr_old)
         code, post = _act_code(activation)
+        if self.precision != "fp32":
+            _checked_static(e_hl, f"e_{h}{l}")
         graph.field = ops.rowmlp(self.up_mlp.pack(),
                                  [(e_hl, None, -1.0), (graph.field, _i32(idx), 1.0), (field_hr_old, None, 1.0)],
-                                 rows=field_hr_old.size(0), act=code)
+                                 rows=field_hr_old.size(0), act=code, precision=_row_precision(self.precision))
         graph.pos = pos_hr
         if post is not None:
             graph.field = post(graph.field)
@@ -284,12 +308,26 @@ def edgeScalarToNodeVector(edge_attr, edge_index, edgeUnitVector=None, edgeUnitV
     return ops.edge_to_node(edge_attr, edgeUnitVectorInverse.contiguous())
 
 
+def interp_layout(y_idx: torch.Tensor):
+    """(n_y, k) of an interpolation list in the layout get_knn_interpolate_weights produces (transforms/interpolate.py:110-129):
+    every target owns k consecutive candidates, y_idx == arange(n_y).repeat_interleave(k).  The kernel (g4c_interp_fwd) relies
+    on it; any other list (batched graphs, fewer than k candidates) is refused instead of being interpolated wrongly."""
+    n_y = int(y_idx.max()) + 1 if y_idx.numel() else 0
+    k = y_idx.numel() // max(n_y, 1)
+    if n_y == 0 or y_idx.numel() != n_y * k or not torch.equal(
+            y_idx, torch.arange(n_y, device=y_idx.device, dtype=y_idx.dtype).repeat_interleave(k)):
+        raise RuntimeError("graphs4cfd_b200: knn_interpolate needs y_idx == arange(n_y).repeat_interleave(k) "
+                           "(uniform k, sorted by target), the layout of get_knn_interpolate_weights")
+    return n_y, k
+
+
 class UpEdgeMP(nn.Module):
     """Mirror of blocks.py:384-456."""
 
     def __init__(self, up_mlp_args: Tuple):
         super().__init__()
         self.up_mlp = MLP(*up_mlp_args)
+        self.precision = _DEFAULT_PRECISION
 
     def forward(self, pos, y_idx_21, x_idx_21, weights_21, edge_attr2, edge_index2, edgeUnitVectorInverse2,
                 coarse_mask2, edge_attr1, edge_index1, edgeUnitVector1, coarse_mask1=None):
@@ -297,8 +335,7 @@ class UpEdgeMP(nn.Module):
         _no_grad_guard(edge_attr2, edge_attr1)
         total = pos.size(0)
         v2 = ops.edge_to_node(edge_attr2, edgeUnitVectorInverse2)
-        n_y, k = _TOPO_CACHE.get(("interp",) + _Cache.key(y_idx_21),
-                                 lambda: (int(y_idx_21.max()) + 1, y_idx_21.numel() // (int(y_idx_21.max()) + 1)))
+        n_y, k = _TOPO_CACHE.get(("interp",) + _Cache.key(y_idx_21), lambda: interp_layout(y_idx_21))
         v1 = torch.zeros(total, v2.size(1), device=v2.device, dtype=torch.float32)
         y_row = None
         if coarse_mask1 is not None:
@@ -307,7 +344,7 @@ class UpEdgeMP(nn.Module):
         ops.interp(v2, _i32(x_idx_21), weights_21.reshape(-1), k, n_y, v1, y_row)
         col1 = _TOPO_CACHE.get(("col",) + _Cache.key(edge_index1), lambda: edge_index1[1].to(torch.int32).contiguous())
         e1 = ops.project(v1, col1, edgeUnitVector1)
-        return ops.rowmlp(self.up_mlp.pack(), [(e1, None, 1.0), (edge_attr1, None, 1.0)])
+        return ops.rowmlp(self.up_mlp.pack(), [(e1, None, 1.0), (edge_attr1, None, 1.0)], precision=_row_precision(self.precision))
 
 
 # --------------------------------------------------------------------------- drop-in plumbing
@@ -320,20 +357,25 @@ def _convert(mod: nn.Module, precision: str):
     if isinstance(mod, tuple(_BY_REF_NAME.values())):
         return mod
     if name == "MLP":
-        return MLP.adopt(mod)
+        new = MLP.adopt(mod)
+        new.precision = precision
+        return new
     cls = _BY_REF_NAME.get(name)
     if cls is None:
         return None
     new = cls.__new__(cls)
     nn.Module.__init__(new)
-    for attr in ("edge_mlp", "node_mlp", "angle_mlp", "down_mlp", "up_mlp"):
-        if hasattr(mod, attr):
-            setattr(new, attr, MLP.adopt(getattr(mod, attr)))
+    # children in the ORIGINAL registration order, so state_dict() keeps the reference's key order (REMuS blocks register
+    # angle_mlp before edge_mlp, blocks.py:307-310)
+    for attr, child in mod.named_children():
+        adopted = MLP.adopt(child) if type(child).__name__ == "MLP" else child
+        if isinstance(adopted, MLP):
+            adopted.precision = precision
+        setattr(new, attr, adopted)
     for attr in ("aggr", "hr_graph_idx", "lr_graph_idx"):
         if hasattr(mod, attr):
             setattr(new, attr, getattr(mod, attr))
-    if hasattr(new, "edge_mlp"):
-        new.precision = precision
+    new.precision = precision
     return new
 
 
@@ -346,9 +388,19 @@ def accelerate(model: nn.Module, precision: str = "auto") -> nn.Module:
         new = _convert(child, precision)
         if new is not None and new is not child:
             setattr(model, name, new)
+    # REMuS forwards call the module-level helper edgeScalarToNodeVector (nn/remus_gnn.py:197).  It is a module global, shared
+    # by every model of that module, so it is wrapped rather than replaced: CUDA tensors take g4c_edge_to_node_fwd, anything
+    # else (another, un-accelerated model living on the CPU) still reaches the reference's own function.
     mod = sys.modules.get(type(model).__module__)
-    if mod is not None and hasattr(mod, "edgeScalarToNodeVector"):
-        mod.edgeScalarToNodeVector = edgeScalarToNodeVector
+    orig = getattr(mod, "edgeScalarToNodeVector", None) if mod is not None else None
+    if orig is not None and orig is not edgeScalarToNodeVector and not getattr(orig, "_g4c_wrapper", False):
+        def dispatch(edge_attr, *args, **kwargs):
+            if edge_attr.is_cuda:
+                return edgeScalarToNodeVector(edge_attr, *args, **kwargs)
+            return orig(edge_attr, *args, **kwargs)
+        dispatch._g4c_wrapper = True
+        dispatch.__wrapped__ = orig
+        mod.edgeScalarToNodeVector = dispatch
     return model
 
 

@@ -10,7 +10,7 @@
 namespace g4c {
 
 static thread_local char g_err[512] = "";
-static std::atomic<int64_t> g_launches{0};
+static std::atomic<int64_t> g_launches{0}, g_tc_launches{0};
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -18,7 +18,10 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
-void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+void count_launch(int n, bool tensor_core) {
+    g_launches.fetch_add(n, std::memory_order_relaxed);
+    if (tensor_core) g_tc_launches.fetch_add(n, std::memory_order_relaxed);
+}
 int check_launch(const char* what) {
     cudaError_t e = cudaPeekAtLastError();
     if (e != cudaSuccess) {
@@ -64,6 +67,7 @@ extern "C" {
 int g4c_version(void) { return G4C_VERSION; }
 const char* g4c_last_error(void) { return g_err; }
 int64_t g4c_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+int64_t g4c_tc_launch_count(void) { return g_tc_launches.load(std::memory_order_relaxed); }
 
 int g4c_rowmlp_fwd(const G4cRowMlpDesc* d, void* stream) {
     if (!d) { set_error("g4c_rowmlp_fwd: NULL descriptor"); return G4C_EINVAL; }

@@ -55,7 +55,7 @@ __device__ __forceinline__ float4 ldg_stream(const float* p) {
 }
 
 void set_error(const char* fmt, ...);
-void count_launch(int n = 1);
+void count_launch(int n = 1, bool tensor_core = false);      // tensor_core: a tcgen05 kernel (g4c_tc_launch_count)
 int check_launch(const char* what);
 
 // ---- per-DEVICE launch configuration.  cudaFuncSetAttribute and the SM count belong to the current device, and a process may

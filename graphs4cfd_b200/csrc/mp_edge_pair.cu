@@ -639,7 +639,7 @@ int edge_pair_launch(const EdgeArgs& a, cudaStream_t st) {
     const int64_t n_units = (a.n_targets + 127) / 128, n_up = (n_units + 1) / 2;
     const int pairs = (int)std::min<int64_t>(n_up, n_sm / 2);
     ep::edge_pair_kernel<<<2 * pairs, ep::NT, smem, st>>>(a);
-    count_launch();
+    count_launch(1, true);
     return check_launch("edge_pair_kernel");
 }
 

@@ -681,7 +681,7 @@ int edge_v5_launch(const EdgeArgs& a, cudaStream_t st) {
     const int64_t n_units = (a.n_targets + 127) / 128, n_up = (n_units + 1) / 2;
     const int pairs = (int)std::min<int64_t>(n_up, n_sm / 2);
     ep5::edge_v5_kernel<<<2 * pairs, ep5::NT, smem, st>>>(a, tm);
-    count_launch();
+    count_launch(1, true);
     return check_launch("edge_v5_kernel");
 }
 

@@ -474,7 +474,7 @@ int row_pair_launch(const G4cRowTcDesc& d, cudaStream_t st) {
     const int n_sm = device_sms();
     const int pairs = (int)std::min<int64_t>(n_pt, n_sm / 2);
     rp::row_pair_kernel<<<2 * pairs, pairk::NT, smem, st>>>(a);
-    count_launch();
+    count_launch(1, true);
     return check_launch("row_pair_kernel");
 }
 

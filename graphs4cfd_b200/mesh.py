@@ -14,8 +14,9 @@ torch_cluster, so the layouts are rebuilt here in vectorised numpy:
 * ``angle_index_down``   = transforms/remus.py:151-176
 * ``knn_interp_weights`` = transforms/interpolate.py:110-129
 
-``tests/test_mesh_layouts.py`` checks every one of them against the reference's own
-transform on the same points (in the build container, where the reference exists).
+``tests/test_oracle_vs_reference.py`` (``test_mus_layouts_match_reference_transforms``,
+``test_remus_layouts_match_reference_transforms``) checks them against the reference's own
+transforms on the same points wherever the reference tree or its staged copy exists.
 """
 import math
 import os
@@ -55,6 +56,57 @@ class Mesh:
 
     def keys(self):
         return list(self.__dict__)
+
+
+# --------------------------------------------------------------------------- plan-time spatial renumbering
+def morton_order(pos: torch.Tensor, bits: int = 24) -> np.ndarray:
+    """Permutation that sorts 2-D points along the Z-order (Morton) curve: perm[i] = index of the point that comes i-th.
+    The hot path gathers P_r[src] rows for every edge; kNN sources are near in SPACE, so a space-filling order makes them
+    near in MEMORY whatever order the caller's mesh came in (hard part 4).  Keys are 2 x `bits` bits of the
+    positions quantised on the bounding box; ties (coincident points) keep their given order."""
+    p = pos[:, :2].detach().double().cpu().numpy()
+    lo = p.min(axis=0)
+    span = max(float((p.max(axis=0) - lo).max()), 1e-30)
+    q = np.minimum((p - lo) / span * float(2 ** bits - 1), float(2 ** bits - 1)).astype(np.uint64)
+
+    def spread(x):                       # abcd -> 0a0b0c0d
+        x = (x | (x << np.uint64(16))) & np.uint64(0x0000FFFF0000FFFF)
+        x = (x | (x << np.uint64(8))) & np.uint64(0x00FF00FF00FF00FF)
+        x = (x | (x << np.uint64(4))) & np.uint64(0x0F0F0F0F0F0F0F0F)
+        x = (x | (x << np.uint64(2))) & np.uint64(0x3333333333333333)
+        x = (x | (x << np.uint64(1))) & np.uint64(0x5555555555555555)
+        return x
+
+    key = spread(q[:, 0]) | (spread(q[:, 1]) << np.uint64(1))
+    return np.argsort(key, kind="stable")
+
+
+def permute_mus_nodes(g: "Mesh", perm) -> "Mesh":
+    """The same MuS mesh with its level-1 nodes renumbered: new node i = old node perm[i].  Every per-node attribute follows
+    its node, edges are regrouped by their new target keeping each target's in-edges in their given relative order (so a
+    node's aggregation order, hence its arithmetic, is unchanged), coarser levels keep their numbering."""
+    perm = torch.as_tensor(np.asarray(perm), dtype=torch.long)
+    n = int(g.pos.shape[0])
+    inv = torch.empty(n, dtype=torch.long)
+    inv[perm] = torch.arange(n)
+    out = Mesh()
+    ei = g.edge_index
+    order = torch.sort(inv[ei[1].cpu()], stable=True).indices
+    # attributes indexed by level-1 node (transforms/mus.py:9-37 stores the level-1 -> level-2 maps per FINE node)
+    level1 = {"pos", "field", "glob", "omega", "loc", "target", "bound", "batch", "cluster_2", "idx1_to_idx2", "e_12"}
+    for key, val in g.__dict__.items():
+        if not torch.is_tensor(val):
+            out.__dict__[key] = val
+        elif key == "edge_index":
+            out.edge_index = inv[ei.cpu()[:, order]].to(ei.device)
+        elif key == "edge_attr":
+            out.edge_attr = val[order.to(val.device)]
+        elif key in level1:
+            assert val.shape[0] == n, key
+            out.__dict__[key] = val[perm.to(val.device)]
+        else:
+            out.__dict__[key] = val
+    return out
 
 
 # --------------------------------------------------------------------------- points

@@ -21,6 +21,21 @@ def _swizzled_images(M: torch.Tensor):
     return out.reshape(K // 64, R, 64)
 
 
+# tcgen05.mma adds every product into its fp32 accumulator with round-toward-zero: each accumulating MMA pulls the running sum
+# toward zero by a fraction of an ulp, a SYSTEMATIC relative shrink that grows with the number of MMAs of a GEMM (measured on
+# B200, tools/tc_bias.py / profiles/r2h_tc_bias.txt: -4.45e-7 for K = 128 = 24 MMAs of the 3-term split, the same for centred
+# and offset inputs; torch's fp32 matmul: -5e-10).  LayerNorm cancels a scale error, but encoders, decoders and hidden layers
+# have none, and a rollout integrates the bias step after step (drift linear in the step count instead of a random walk).
+# The kernels multiply the accumulator by 1/s anyway, so the expected shrink is folded into that factor: exact on average,
+# no instruction added.  kappa = relative shrink per accumulating MMA.
+TC_RZ_KAPPA = 4.45e-7 / 24.0
+
+
+def rz_compensation(n_mma: int) -> float:
+    """Factor that undoes the mean round-toward-zero shrink of an accumulator that received ``n_mma`` MMAs."""
+    return 1.0 + TC_RZ_KAPPA * n_mma
+
+
 def weight_scale(W: torch.Tensor) -> float:
     """Power-of-two s keeping |s*W| below 1024 so the fp16 residual of s*W stays a normal number."""
     amax = float(W.abs().max())
@@ -152,7 +167,7 @@ class EdgePairPack:
         self.W_pair, self.inv_scale = [], []
         pk, inv = pack_weight_pair(W1[:, :128].contiguous(), s1)
         self.W_pair.append(pk)
-        self.inv_scale.append(inv)
+        self.inv_scale.append(inv * rz_compensation(24))          # K = 128: 8 K-steps x 3 split products
         self.p_scale = s1
         self.W1s = W1[:, 128:256].contiguous()
         self.W1t = W1[:, 256:384].contiguous()
@@ -162,7 +177,7 @@ class EdgePairPack:
             assert W.shape == (128, 128)
             pk, inv = pack_weight_pair(W)
             self.W_pair.append(pk)
-            self.inv_scale.append(inv)
+            self.inv_scale.append(inv * rz_compensation(24))
             self.bias.append(b.detach().float().contiguous().clone())
         self.ln = None if ln is None else (ln[0].detach().float().contiguous().clone(),
                                            ln[1].detach().float().contiguous().clone())
@@ -204,7 +219,9 @@ class RowPairPack:
                 assert W.shape[0] == 128
             pk, inv = pack_weight_pair(W.contiguous())
             self.W_pair.append(pk)
-            self.inv_scale.append(inv * self.out_scale)           # out = out_scale * (x W^T + b)
+            # MMAs into this layer's accumulator: 3 split products per K = 16 step; a 128-wide segment has 8 steps, a narrow one 1
+            n_mma = 3 * (sum(8 if w == 128 else 1 for w in seg_widths) if i == 0 else 8)
+            self.inv_scale.append(inv * self.out_scale * rz_compensation(n_mma))           # out = out_scale * (x W^T + b)
             self.bias.append((b * self.out_scale).contiguous().clone())
         self.ln = None if ln is None else (ln[0].detach().float().contiguous().clone(),
                                            ln[1].detach().float().contiguous().clone())
@@ -233,7 +250,7 @@ def rowmlp_tc(pack: RowPairPack, segs, rows: Optional[int] = None, act=None, out
     d.out, d.out_stride = out.data_ptr(), int(out.stride(0))
     if residual is not None:
         d.residual, d.res_stride = residual.data_ptr(), int(residual.stride(0))
-    L.check(L.lib().g4c_rowmlp_tc_fwd(C.byref(d), L.stream_ptr()))
+    L.launch("g4c_rowmlp_tc_fwd", d, out, residual, *tens, *[s[1] for s in segs])
     return out
 
 
@@ -253,7 +270,7 @@ def dual_linear_tc(pack_a: RowPairPack, pack_b: RowPairPack, x: torch.Tensor, ou
         out_b = torch.empty(rows, 128, device=x.device, dtype=torch.float32)
     assert out_a.stride(0) == out_b.stride(0)
     d.out, d.out2, d.out_stride = out_a.data_ptr(), out_b.data_ptr(), int(out_a.stride(0))
-    L.check(L.lib().g4c_rowmlp_tc_fwd(C.byref(d), L.stream_ptr()))
+    L.launch("g4c_rowmlp_tc_fwd", d, x, out_a, out_b)
     return out_a, out_b
 
 
@@ -287,8 +304,25 @@ def edge_aggr(pack: EdgePairPack, topo: "MpTopo", e_in, P_r, P_c, aggr="mean", a
     d.variant = EDGE_VARIANTS[EDGE_VARIANT_DEFAULT if variant is None else variant]
     if pack.ln is not None:
         d.gamma, d.beta = pack.ln[0].data_ptr(), pack.ln[1].data_ptr()
-    L.check(L.lib().g4c_edge_aggr_fwd(C.byref(d), L.stream_ptr()))
+    L.launch("g4c_edge_aggr_fwd", d, e_in, P_r, P_c, e_out, agg_out, topo.src, topo.rowptr, topo.edge_perm, topo.tgt_perm)
     return agg_out, (e_out if want_e else None)
+
+
+FP16_SPLIT_MAX = 3.0e4      # |x| the fp16 (hi, lo) operand split accepts with a factor 2 of head-room (fp16 max 65504)
+
+
+def check_fp16_range(t: torch.Tensor, what: str):
+    """The tensor-core path splits activations into fp16 (hi, lo) without a per-tensor scale: LayerNorm / SELU / tanh
+    outputs are O(1) by construction, but RAW inputs (fields, relative positions, encoder inputs) are whatever the caller
+    passes.  |x| > 65504 would become inf (then NaN through the lo term).  Called once per plan / solve (it synchronises),
+    never per step.  Values below 6e-5 keep an ABSOLUTE accuracy of 3e-8 (fp16 subnormal lo term), which is what a dot
+    product with O(1) partners needs."""
+    if t.numel() == 0:
+        return
+    amax = float(t.detach().abs().max())
+    if not (amax <= FP16_SPLIT_MAX):          # also catches NaN
+        raise RuntimeError(f"graphs4cfd_b200: {what} has |x| up to {amax:.3g}; the fp16x3 tensor-core path accepts raw inputs "
+                           f"up to {FP16_SPLIT_MAX:.0e} (rescale the input, or use precision='fp32')")
 
 
 class MpTopo:
@@ -358,7 +392,7 @@ def rowmlp(pack: MlpPack, segs, rows: Optional[int] = None, act=None, out=None, 
     d.out, d.out_stride = out.data_ptr(), int(out.stride(0))
     if residual is not None:
         d.residual, d.res_stride = residual.data_ptr(), int(residual.stride(0))
-    L.check(L.lib().g4c_rowmlp_fwd(C.byref(d), L.stream_ptr()))
+    L.launch("g4c_rowmlp_fwd", d, out, residual, *tens, *[s[1] for s in segs])
     return out
 
 
@@ -409,7 +443,7 @@ def mp(edge_pack: MlpPack, node_pack: MlpPack, topo: MpTopo, e_in, src_feat, tgt
     d.e_out = e_out.data_ptr() if want_e else 0
     d.t_out = t_out.data_ptr()
     d.edge_mlp, d.node_mlp = edge_pack.struct(), node_pack.struct()
-    L.check(L.lib().g4c_mp_fwd(C.byref(d), L.stream_ptr()))
+    L.launch("g4c_mp_fwd", d, e_in, src_feat, tgt_feat, e_out, t_out, topo.src, topo.rowptr, topo.edge_perm, topo.tgt_perm)
     return t_out, (e_out if want_e else None)
 
 
@@ -422,7 +456,7 @@ def seg_reduce(x, ptr, idx, n_groups, aggr="mean", act=None, out=None):
     if out is None:
         out = torch.empty(n_groups, x.shape[1], device=x.device, dtype=torch.float32)
     d.out = out.data_ptr()
-    L.check(L.lib().g4c_seg_reduce_fwd(C.byref(d), L.stream_ptr()))
+    L.launch("g4c_seg_reduce_fwd", d, x, ptr, idx, out)
     return out
 
 
@@ -438,7 +472,7 @@ def project(V, col, U, extras=(), out=None):
     if out is None:
         out = torch.empty(col.numel(), F + len(extras), device=V.device, dtype=torch.float32)
     d.out = out.data_ptr()
-    L.check(L.lib().g4c_project_fwd(C.byref(d), L.stream_ptr()))
+    L.launch("g4c_project_fwd", d, V, col, U, out, *extras)
     return out
 
 
@@ -454,7 +488,7 @@ def edge_to_node(e, Uinv, out=None, residual=None):
     d.V, d.out_stride = out.data_ptr(), int(out.stride(0))
     if residual is not None:
         d.residual, d.res_stride = residual.data_ptr(), int(residual.stride(0))
-    L.check(L.lib().g4c_edge_to_node_fwd(C.byref(d), L.stream_ptr()))
+    L.launch("g4c_edge_to_node_fwd", d, e, Uinv, out, residual)
     return out
 
 
@@ -464,7 +498,7 @@ def interp(x, x_idx, w, k, n_out, y, y_row=None):
     d.n_out, d.k, d.width = int(n_out), int(k), int(x.shape[1])
     d.x_idx, d.w, d.x, d.y = x_idx.data_ptr(), w.data_ptr(), x.data_ptr(), y.data_ptr()
     d.y_row = 0 if y_row is None else y_row.data_ptr()
-    L.check(L.lib().g4c_interp_fwd(C.byref(d), L.stream_ptr()))
+    L.launch("g4c_interp_fwd", d, x, x_idx, w, y, y_row)
     return y
 
 
@@ -473,14 +507,14 @@ def step_update(pred, node_in, field_width, outputs, t):
     d.n_nodes, d.nf, d.field_width = int(pred.shape[0]), int(pred.shape[1]), int(field_width)
     d.in_stride, d.out_stride, d.t = int(node_in.stride(0)), int(outputs.stride(0)), int(t)
     d.pred, d.node_in, d.outputs = pred.data_ptr(), node_in.data_ptr(), outputs.data_ptr()
-    L.check(L.lib().g4c_step_update(C.byref(d), L.stream_ptr()))
+    L.launch("g4c_step_update", d, pred, node_in, outputs)
 
 
 def halo_pack(src, idx, dst):
     d = L.HaloDesc()
     d.n_rows, d.width = int(idx.numel()), int(src.shape[1])
     d.idx, d.src, d.dst = idx.data_ptr(), src.data_ptr(), dst.data_ptr()
-    L.check(L.lib().g4c_halo_pack(C.byref(d), L.stream_ptr()))
+    L.launch("g4c_halo_pack", d, src, idx, dst)
     return dst
 
 
@@ -488,7 +522,7 @@ def halo_unpack(buf, idx, dst):
     d = L.HaloDesc()
     d.n_rows, d.width = int(idx.numel()), int(dst.shape[1])
     d.idx, d.src, d.dst = idx.data_ptr(), buf.data_ptr(), dst.data_ptr()
-    L.check(L.lib().g4c_halo_unpack(C.byref(d), L.stream_ptr()))
+    L.launch("g4c_halo_unpack", d, buf, idx, dst)
     return dst
 
 

@@ -338,6 +338,16 @@ class _CudaBackend:
         self.eng = eng
         self.pool: Dict = {}
         self.steps = []
+        self.labels = []          # one label per step function (tools/partition_timeline.py)
+        self._pending = None      # a halo exchange not emitted yet: the message-passing block that follows may overlap it
+        self._ws: Dict = {}       # per level: (P_r, P_c, agg) of the tensor-core block
+
+    def _flush(self):
+        if self._pending is not None:
+            _, _, start, label = self._pending
+            self._pending = None
+            self.steps.append(lambda: start(False))
+            self.labels.append(label)
 
     def alloc(self, level, kind):
         P = self.eng.plan["levels"][level]
@@ -360,20 +370,62 @@ class _CudaBackend:
         eng = self.eng
         res = eng.node_in[:, eng.field_width - eng.nf:eng.field_width] if residual else None
         pack = eng.pack(prefix)
-        self.steps.append(lambda: ops.rowmlp(pack, segs, rows=rows, act=act, out=out, residual=res))
+        precision = "auto" if eng.precision == "fp16x3" else "fp32"      # "auto": tensor-core kernel where it supports the shape
+        self._flush()
+        self.steps.append(lambda: ops.rowmlp(pack, segs, rows=rows, act=act, out=out, residual=res, precision=precision))
+        self.labels.append(f"rowmlp {prefix} rows={rows}")
 
     def mp(self, name, level, e_in, v_in, e_out, v_out):
         from . import ops
         eng = self.eng
         ep, npk, topo = eng.pack(name + ".edge_mlp"), eng.pack(name + ".node_mlp"), eng.topos[level]
         eng.mp_args.append(dict(ep=ep, np_=npk, topo=topo, e_in=e_in, v_in=v_in, e_out=e_out, v_out=v_out))    # for bench.py's roofline
+        pend = self._pending
+        if (pend is not None and pend[0] is v_in and eng.overlap and eng.precision == "fp16x3" and ep.tc_edge_ok()
+                and npk.tc_row_ok([128, 128]) and pend[1].recv_off == topo.n_targets):
+            # Tensor-core block with its halo exchange in flight behind the first kernel: the ghost rows are only SOURCES, and a
+            # source enters the edge model through its product P_r = S W1s^T (mp_edge_pair.cu), so
+            #   pack + all_to_all (NCCL stream)   ||   P_r, P_c of the OWN rows (one pass over v, compute stream)
+            #   then P_r of the ghost rows (a few hundred rows), the fused edge kernel, the node model of the own rows.
+            self._pending = None
+            _, x, start, _ = pend
+            n_own, g0, g1 = topo.n_targets, pend[1].recv_off, pend[1].recv_off + pend[1].n_recv
+            epk, proj_s, proj_t = ep.tc_edge()
+            node_pk = npk.tc_row([128, 128])
+            ws = self._ws.get(level)
+            if ws is None:
+                mk = lambda n: torch.empty(max(n, 1), 128, device=eng.device, dtype=torch.float32)
+                ws = self._ws[level] = (mk(v_in.shape[0]), mk(n_own), mk(n_own))
+                eng.buffer_bytes += sum(t.numel() * 4 for t in ws)
+            P_r, P_c, agg = ws
+
+            def run():
+                work = start(True)
+                if n_own:
+                    ops.dual_linear_tc(proj_s, proj_t, v_in[:n_own], out_a=P_r[:n_own], out_b=P_c[:n_own])
+                if work is not None:
+                    work.wait()
+                if g1 > g0:
+                    ops.rowmlp_tc(proj_s, [(v_in[g0:g1], None, 1.0)], out=P_r[g0:g1])
+                if n_own:
+                    ops.edge_aggr(epk, topo, e_in, P_r, P_c, aggr="mean", act_e="selu", want_e=e_out is not None,
+                                  e_out=e_out, agg_out=agg, p_prescaled=True)
+                    ops.rowmlp_tc(node_pk, [(agg[:n_own], None, 1.0), (v_in[:n_own], None, 1.0)], act="selu", out=v_out[:n_own])
+
+            self.steps.append(run)
+            self.labels.append(f"mp+halo {name} level={level} targets={topo.n_targets} edges={topo.n_edges} ghosts={g1 - g0}")
+            return
+        self._flush()
         self.steps.append(lambda: ops.mp(ep, npk, topo, e_in, v_in, v_in, act_e="selu", act_t="selu",
                                          want_e=e_out is not None, precision=eng.precision, e_out=e_out, t_out=v_out))
+        self.labels.append(f"mp {name} level={level} targets={topo.n_targets} edges={topo.n_edges}")
 
     def seg(self, x, csr, n, act, out):
         from . import ops
         ptr, idx = csr
+        self._flush()
         self.steps.append(lambda: ops.seg_reduce(x, ptr, idx, n, "mean", act, out=out))
+        self.labels.append(f"seg_reduce groups={n}")
 
     def xchg(self, buf, x: Xchg):
         if not x.active:
@@ -385,22 +437,35 @@ class _CudaBackend:
         stage = torch.empty(max(x.n_send, 1), eng.H, device=eng.device, dtype=torch.float32)
         eng.buffer_bytes += stage.numel() * 4
 
-        def run():
+        def start(async_op):
             if x.n_send:
                 ops.halo_pack(buf, send_idx, stage)
-            dist.all_to_all_single(buf[x.recv_off:x.recv_off + x.n_recv], stage[:x.n_send], x.recv_splits, x.send_splits)
+            return dist.all_to_all_single(buf[x.recv_off:x.recv_off + x.n_recv], stage[:x.n_send], x.recv_splits, x.send_splits,
+                                          async_op=async_op)
 
-        self.steps.append(run)
+        self._flush()
+        self._pending = (buf, x, start, f"halo exchange send={x.n_send} recv={x.n_recv} rows")
         eng.exchanges_per_step += 1
 
 
 class PartitionedRollout:
     """Rank-local slice of a MuS-GNN rollout.  API mirrors Rollout (solve / step_only / pred / node_in)."""
 
-    def __init__(self, params, graph, rank: int, world: int, precision="auto", device="cuda", cuda_graph=False):
+    def __init__(self, params, graph, rank: int, world: int, precision="auto", device="cuda", cuda_graph=False, renumber=True,
+                 overlap=True):
+        """overlap: the halo exchange of a tensor-core message-passing block runs on NCCL's stream behind the block's first
+        kernel (the per-node products of the own rows) instead of in front of the block."""
         from . import ops
+        self.overlap = overlap
         self.device = torch.device(device)
         self.rank, self.world, self.precision = rank, world, precision
+        node_perm = None
+        if renumber and graph.pos.shape[0] > 1:
+            # same plan-time Morton renumbering as Rollout (mesh.morton_order): rows owned by a rank are then stored along the
+            # curve inside its strip; `own` (used by gather) maps back to the caller's node ids
+            from .mesh import morton_order, permute_mus_nodes
+            node_perm = morton_order(graph.pos)
+            graph = permute_mus_nodes(graph, node_perm)
         self.params = {k: v.to(self.device) for k, v in params.items()}
         self.H = hidden_width(self.params)
         if self.precision == "auto":
@@ -416,7 +481,7 @@ class PartitionedRollout:
         self.field0 = self.node_in[:, :self.field_width].clone()
         self.N = int(L[0]["n_own"])
         self.nf = int(self.pack("node_decoder").out_width)
-        self.own = torch.from_numpy(L[0]["own"])
+        self.own = torch.from_numpy(L[0]["own"] if node_perm is None else node_perm[L[0]["own"]])
         i32 = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev, torch.int32)
         self.topos = []
         for P in L:
@@ -431,14 +496,19 @@ class PartitionedRollout:
         self.mp_args = []
         e0_rows = L[0]["eglob"].size + L[0].get("n_edge_recv", 0)
         self.e0 = torch.zeros(max(e0_rows, 1), self.H, device=dev, dtype=torch.float32)
-        ops.rowmlp(self.pack("edge_encoder"), [(edge_attr.to(dev), None, 1.0)], act="selu", out=self.e0)
+        row_prec = "auto" if self.precision == "fp16x3" else "fp32"
+        if self.precision == "fp16x3":
+            ops.check_fp16_range(edge_attr, "edge_attr")
+            ops.check_fp16_range(self.node_in, "the node inputs (field, loc, glob, omega)")
+        ops.rowmlp(self.pack("edge_encoder"), [(edge_attr.to(dev), None, 1.0)], act="selu", out=self.e0, precision=row_prec)
         self.e0._g4c_key = ("e0",)
         self.pred = torch.empty(max(self.N, 1), self.nf, device=dev, dtype=torch.float32)
         be = _CudaBackend(self)
         be.node_in, be.e0, be.e_hl, be.children, be.pool, be.parent_local, be.pred = \
             self.node_in, self.e0, self.e_hl, self.children, self.pool, self.parent_local, self.pred
         run_step_program(be, plan, self.prog)
-        self._steps = be.steps
+        be._flush()
+        self._steps, self.step_labels = be.steps, be.labels
         self.launches_per_step = len(be.steps) + 1
         self.use_graph, self._graph = cuda_graph, None
 
@@ -455,14 +525,21 @@ class PartitionedRollout:
                 fn()
             return
         if self._graph is None:
+            from . import ops
+            n0 = ops.L.launch_count()
             for fn in self._steps:
                 fn()
+            self.launches_per_step = ops.L.launch_count() - n0 + 1          # libg4c kernels per step (+ step_update)
             torch.cuda.synchronize(self.device)
             self._graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self._graph):
                 for fn in self._steps:
                     fn()
         self._graph.replay()
+
+    def release_graph(self):
+        """Drop the captured step graph (it holds NCCL kernels; do this before the process group is destroyed)."""
+        self._graph = None
 
     def solve(self, n_out: int) -> torch.Tensor:
         """Local rows of the rollout output [n_own, nf*n_out]; `gather` assembles the global tensor."""
@@ -491,5 +568,6 @@ def partitioned_rollout(params, graph, rank: int, world: int, **kw):
     nn/remus_gnn.py:19-57) get the edge-halo partition of partition_remus.py, everything else the node-halo one."""
     if any(k.startswith("angle_encoder") for k in params):
         from .partition_remus import PartitionedRemusRollout
+        kw = {k: v for k, v in kw.items() if k not in ("overlap", "renumber")}      # MuS-engine options
         return PartitionedRemusRollout(params, graph, rank, world, **kw)
     return PartitionedRollout(params, graph, rank, world, **kw)

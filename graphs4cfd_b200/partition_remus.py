@@ -408,6 +408,7 @@ class PartitionedRemusRollout:
         self.mp_args = []
         be = _CudaBackend(self)
         be.a_static, be.a_dn = {}, {}
+        row_prec = "auto" if self.precision == "fp16x3" else "fp32"
         for l in (1, 2, 3):
             P = L[l]
             n_e = P["n_own"] * k
@@ -415,7 +416,8 @@ class PartitionedRemusRollout:
             self.col1[l], self.U[l], self.Uinv[l] = i32(P["col1"]), f32(P["U"]), f32(P["Uinv"])
             be.a_static[l] = torch.zeros(max(n_e * k, 1), self.H, device=dev)
             if n_e:
-                ops.rowmlp(self.pack("angle_encoder" + SFX[l]), [(f32(P["angle_attr"]), None, 1.0)], act="selu", out=be.a_static[l])
+                ops.rowmlp(self.pack("angle_encoder" + SFX[l]), [(f32(P["angle_attr"]), None, 1.0)], act="selu", out=be.a_static[l],
+                           precision=row_prec)
             self.buffer_bytes += be.a_static[l].numel() * 4
         for lo, name in ((1, "12"), (2, "23")):
             P = L[lo + 1]
@@ -423,7 +425,8 @@ class PartitionedRemusRollout:
             self.topos[("dn", lo)] = ops.MpTopo(n_e, n_e * k, i32(P["dn_src"]), fixed_k=k)
             be.a_dn[lo] = torch.zeros(max(n_e * k, 1), self.H, device=dev)
             if n_e:
-                ops.rowmlp(self.pack("angle_encoder" + name), [(f32(P["dn_attr"]), None, 1.0)], act="selu", out=be.a_dn[lo])
+                ops.rowmlp(self.pack("angle_encoder" + name), [(f32(P["dn_attr"]), None, 1.0)], act="selu", out=be.a_dn[lo],
+                           precision=row_prec)
             self.buffer_bytes += be.a_dn[lo].numel() * 4
         for hi in (2, 1):
             P = L[hi]
@@ -450,14 +453,21 @@ class PartitionedRemusRollout:
                 fn()
             return
         if self._graph is None:
+            from . import ops
+            n0 = ops.L.launch_count()
             for fn in self._steps:
                 fn()
+            self.launches_per_step = ops.L.launch_count() - n0 + 1          # libg4c kernels per step (+ step_update)
             torch.cuda.synchronize(self.device)
             self._graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self._graph):
                 for fn in self._steps:
                     fn()
         self._graph.replay()
+
+    def release_graph(self):
+        """Drop the captured step graph (it holds NCCL kernels; do this before the process group is destroyed)."""
+        self._graph = None
 
     def solve(self, n_out: int) -> torch.Tensor:
         """Local rows of the rollout output [n_own, 2*n_out]; `gather` assembles the global tensor."""

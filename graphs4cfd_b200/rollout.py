@@ -13,6 +13,7 @@ At construction the engine turns (state_dict, static mesh attributes) into a pla
 """
 from typing import Dict, List, Optional
 
+import numpy as np
 import torch
 
 from . import ops
@@ -56,7 +57,12 @@ class _Level:
 
 
 class Rollout:
-    def __init__(self, model_or_params, graph, precision: str = "auto", device="cuda", cuda_graph: bool = True):
+    def __init__(self, model_or_params, graph, precision: str = "auto", device="cuda", cuda_graph: bool = True,
+                 renumber: bool = True):
+        """renumber: MuS-GNN plans renumber the level-1 nodes along a Morton curve of ``graph.pos`` (mesh.morton_order) so
+        that gathered source rows are near in memory whatever order the mesh came in; inputs (``set_field``) and outputs
+        (``solve``) stay in the caller's node order, ``node_in`` / ``pred`` / ``field0`` are in ENGINE order
+        (``node_perm[i]`` = caller's index of engine row i)."""
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("Rollout needs a CUDA device; graphs4cfd_b200 has no CPU path")
@@ -71,10 +77,17 @@ class Rollout:
         self.use_graph = cuda_graph
         self._graph = None
         self.launches_per_step = 0
+        self.node_perm = None
         if is_remus(self.params):
             from .rollout_remus import plan_remus
             plan_remus(self, graph)
         else:
+            if renumber and hasattr(graph, "pos") and graph.pos is not None and graph.pos.shape[0] > 1:
+                from .mesh import morton_order, permute_mus_nodes
+                perm = morton_order(graph.pos)
+                if not np.array_equal(perm, np.arange(perm.size)):
+                    graph = permute_mus_nodes(graph, perm)
+                    self.node_perm = torch.from_numpy(perm).to(self.device)
             self._plan_mus(graph)
 
     # ------------------------------------------------------------------ helpers
@@ -89,6 +102,17 @@ class Rollout:
         if dtype is not None:
             t = t.to(dtype)
         return t.contiguous()
+
+    def check_raw(self, t, what):
+        """Plan-time range check of a RAW input of the fp16x3 path (ops.check_fp16_range; synchronises, once per plan)."""
+        if self.precision == "fp16x3":
+            ops.check_fp16_range(t, what)
+
+    def static_mlp(self, prefix, x, act="selu", out=None):
+        """Encoder of a static input, evaluated once per plan with the ENGINE's precision (nn/mus_gnn.py:317,
+        nn/remus_gnn.py:136-140 recompute it every step)."""
+        pack, segs = self.pack(prefix), [(x, None, 1.0)]
+        return ops.rowmlp(pack, segs, act=act, out=out, precision=self._row_precision(pack, segs, None))
 
     # ------------------------------------------------------------------ MuS plan
     def _plan_mus(self, g):
@@ -114,11 +138,14 @@ class Rollout:
             ea = ea[lv.topo.edge_perm.long()].contiguous()
             ei = ei[:, lv.topo.edge_perm.long()]
             lv.topo.edge_perm = None
-        self.e0 = ops.rowmlp(self.pack("edge_encoder"), [(ea, None, 1.0)], act="selu")
+        self.check_raw(ea, "edge_attr")
+        self.check_raw(self.node_in, "the node inputs (field, loc, glob, omega)")
+        self.e0 = self.static_mlp("edge_encoder", ea)
         for l in range(1, n_down + 1):
             idx = getattr(g, f"idx{l}_to_idx{l + 1}").to(dev)
             cur = levels[-1]
             cur.e_hl = self._dev(getattr(g, f"e_{l}{l + 1}").float())
+            self.check_raw(cur.e_hl, f"e_{l}{l + 1}")
             cur.parent = idx.to(torch.int32).contiguous()
             n_l, cptr, cidx = children_csr(idx)
             cur.children = (cptr, cidx)
@@ -264,22 +291,41 @@ class Rollout:
         self._graph.replay()
 
     def set_field(self, field: torch.Tensor):
-        """Load a new initial field [N, nf*n_in] (host or device)."""
-        self.node_in[:, :self.field_width].copy_(field.to(self.device, torch.float32))
+        """Load a new initial field [N, nf*n_in] (host or device) given in the CALLER's node order."""
+        field = field.to(self.device, torch.float32)
+        self.node_in[:, :self.field_width].copy_(field if self.node_perm is None else field[self.node_perm])
+
+    def _set_field_engine_order(self, field: torch.Tensor):
+        self.node_in[:, :self.field_width].copy_(field)
 
     def solve(self, n_out: int, field: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Roll the model out for n_out steps; returns [N, nf*n_out] on the device (original node order).
         The engine's own input state is restored afterwards, like GNN.solve restores graph.field."""
         assert n_out > 0, "n_out must be greater than 0."
         with torch.no_grad(), torch.cuda.device(self.device):
-            self.set_field(self.field0 if field is None else field)
+            if field is None:
+                self._set_field_engine_order(self.field0)
+            else:
+                self.set_field(field)
             outputs = torch.empty(self.N, self.nf * n_out, device=self.device, dtype=torch.float32)
+            if self.precision == "fp16x3":
+                ops.check_fp16_range(self.node_in[:, :self.field_width], "the initial field")
             for t in range(n_out):
                 self._step()
                 ops.step_update(self.pred, self.node_in, self.field_width, outputs, t)
-            self.set_field(self.field0)
+            self._set_field_engine_order(self.field0)
+            if self.precision == "fp16x3":
+                # every prediction was the next step's raw input: one deferred check instead of a sync per step
+                ops.check_fp16_range(outputs, "a predicted field of this rollout")
+            if self.node_perm is not None:            # back to the caller's node order
+                ordered = torch.empty_like(outputs)
+                ordered[self.node_perm] = outputs
+                outputs = ordered
         return outputs
 
     def step_only(self):
         """One time step without the output bookkeeping (used by the benchmark's timed loop)."""
         self._step()
+
+    def release_graph(self):
+        self._graph = None

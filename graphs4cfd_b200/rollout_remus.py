@@ -50,20 +50,22 @@ def plan_remus(eng, g):
         attr = f32(getattr(g, "angle_attr" + sfx[l]))
         if perm is not None:
             attr = attr[perm].contiguous()
-        a_static[l] = ops.rowmlp(eng.pack("angle_encoder" + sfx[l]), [(attr, None, 1.0)], act="selu")
+        eng.check_raw(attr, "angle_attr" + sfx[l])
+        a_static[l] = eng.static_mlp("angle_encoder" + sfx[l], attr)
     topo_dn, a_dn = {}, {}
     for lo, name in ((1, "12"), (2, "23")):
         topo_dn[lo], perm = _fixed_k_topo(getattr(g, "angle_index" + name), E[lo + 1], dev)
         attr = f32(getattr(g, "angle_attr" + name))
         if perm is not None:
             attr = attr[perm].contiguous()
-        a_dn[lo] = ops.rowmlp(eng.pack("angle_encoder" + name), [(attr, None, 1.0)], act="selu")
+        eng.check_raw(attr, "angle_attr" + name)
+        a_dn[lo] = eng.static_mlp("angle_encoder" + name, attr)
     interp = {}
     for hi, name, mask in ((2, "32", g.coarse_mask2), (1, "21", None)):
-        y_idx = getattr(g, "y_idx_" + name)
-        n_y = int(y_idx.max()) + 1
+        from .blocks import interp_layout
+        n_y, k_it = interp_layout(getattr(g, "y_idx_" + name))          # refuses lists that are not uniform-k and sorted
         interp[hi] = dict(x_idx=i32(getattr(g, "x_idx_" + name)), w=f32(getattr(g, "weights_" + name)).reshape(-1),
-                          k=int(y_idx.numel() // n_y), n_y=n_y,
+                          k=k_it, n_y=n_y,
                           y_row=None if mask is None else i32(mask.nonzero().squeeze(1)))
     vfull = torch.zeros(eng.N, 2 * H, device=dev, dtype=torch.float32)   # UpEdgeMP scratch (blocks.py:443)
 

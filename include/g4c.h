@@ -282,6 +282,8 @@ G4C_API int g4c_halo_unpack(const G4cHaloDesc* d, void* stream);
 
 /* number of kernels this library has launched since load (bench.py reports it as gpu_launches) */
 G4C_API int64_t g4c_launch_count(void);
+/* ... of which tensor-core (tcgen05) kernels: g4c_edge_aggr_fwd, g4c_rowmlp_tc_fwd */
+G4C_API int64_t g4c_tc_launch_count(void);
 
 /* self tests of the second-generation primitives (A operand in TMEM, tcgen05.cp, CTA pairs); see
  * graphs4cfd_b200/csrc/tc2_test.cu for the meaning of test / flags.  Used by tests/test_gpu_tc2.py. */

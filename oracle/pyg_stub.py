@@ -230,16 +230,35 @@ def install():
 
 
 REFERENCE_ROOT = '/root/reference'
+# copy staged by tools/stage_reference.py (git-ignored; travels to the GPU box with the repo snapshot)
+STAGED_ROOT = __import__('os').path.join(__import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))),
+                                         'baseline', '_ref')
+
+
+def reference_root():
+    """Directory holding the unmodified reference package: the read-only tree in the build container, else the staged copy."""
+    import os
+    for root in (REFERENCE_ROOT, STAGED_ROOT):
+        if os.path.isdir(os.path.join(root, 'graphs4cfd')):
+            return root
+    return None
+
+
+def staged_checkpoint(name):
+    """Path of a weights-only copy of a shipped checkpoint (tools/stage_reference.py), or None."""
+    import os
+    p = os.path.join(STAGED_ROOT, 'weights', name)
+    return p if os.path.exists(p) else None
 
 
 def import_reference():
-    """Import the UNMODIFIED reference package from /root/reference under the stub.
-    Only possible in the build container (the path does not exist on the GPU box)."""
-    import os
-    if not os.path.isdir(os.path.join(REFERENCE_ROOT, 'graphs4cfd')):
-        raise ImportError("reference tree /root/reference is not present on this machine")
+    """Import the UNMODIFIED reference package under the stub: from /root/reference in the build container, from the
+    staged byte-for-byte copy (baseline/_ref, see tools/stage_reference.py) elsewhere."""
+    root = reference_root()
+    if root is None:
+        raise ImportError("no reference tree: neither /root/reference nor baseline/_ref (python tools/stage_reference.py) is present")
     install()
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+    if root not in sys.path:
+        sys.path.insert(0, root)
     import graphs4cfd  # noqa: E402
     return graphs4cfd

@@ -9,16 +9,17 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-HAVE_REFERENCE = os.path.isdir("/root/reference/graphs4cfd")
+# the read-only tree of the build container, or the byte-for-byte copy staged by tools/stage_reference.py (travels to the GPU box)
+HAVE_REFERENCE = os.path.isdir("/root/reference/graphs4cfd") or os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "graphs4cfd"))
 
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
-    config.addinivalue_line("markers", "reference: needs the /root/reference tree (build container only)")
+    config.addinivalue_line("markers", "reference: needs the reference tree (/root/reference or its staged copy baseline/_ref)")
 
 
 def pytest_collection_modifyitems(config, items):
-    skip_ref = pytest.mark.skip(reason="/root/reference not present on this machine")
+    skip_ref = pytest.mark.skip(reason="no reference tree on this machine (python tools/stage_reference.py)")
     skip_gpu = pytest.mark.skip(reason="no CUDA device")
     for item in items:
         if "reference" in item.keywords and not HAVE_REFERENCE:
@@ -43,3 +44,15 @@ def rel_l2(a, b):
 @pytest.fixture
 def golden():
     return load_golden
+
+
+def shipped_model(gfd, kind, device="cpu"):
+    """The reference's own model class with the reference's trained weights: kind "mus3" = 3S-GNN-NsCircle-v1
+    (nn/mus_gnn.py:267), "remus" = RE3S-GNN-NsEllipse-v1 (nn/remus_gnn.py:66).  Loaded from the weights-only copies staged
+    by tools/stage_reference.py when they exist (the GPU box), else from the reference tree itself."""
+    from oracle.pyg_stub import staged_checkpoint
+    cls, chk, name = {"mus3": (gfd.nn.NsThreeScaleGNN, "NsThreeScaleGNN.chk", "3S-GNN-NsCircle-v1"),
+                      "remus": (gfd.nn.NsRotEquiTreeScaleGNN, "NsRotEquiThreeScaleGNN.chk", "RE3S-GNN-NsEllipse-v1")}[kind]
+    path = staged_checkpoint(chk)
+    dev = torch.device(device)
+    return cls(checkpoint=path, device=dev) if path else cls(model=name, device=dev)

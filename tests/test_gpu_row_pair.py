@@ -113,3 +113,30 @@ def test_dual_linear(rows):
         assert err < 2e-5, f"rel-L2 {err:.3e}"
     # and bit-identical to the single-output kernel
     assert torch.equal(ya, ops.rowmlp_tc(pa, [(x, None, 1.0)])) and torch.equal(yb, ops.rowmlp_tc(pb, [(x, None, 1.0)]))
+
+
+@gpu
+@pytest.mark.parametrize("magnitude", [2.0e4, 1.0, 1.0e-3, 1.0e-6])
+def test_encoder_raw_input_range(magnitude):
+    """The fp16 (hi, lo) operand split takes raw encoder inputs unscaled.  Up to the documented limit (3e4, ops.FP16_SPLIT_MAX)
+    the product keeps its accuracy relative to the OUTPUT scale; tiny inputs (below 6e-5 the lo term is an fp16 subnormal)
+    keep an absolute accuracy of ~3e-8 per operand, which a dot product against O(1) weights turns into < 1e-6."""
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(11)
+    rows, kin = 3000, 5
+    W, b = _lin(kin, 128, g, dev)
+    x = ((torch.rand(rows, kin, generator=g) * 2 - 1) * magnitude).to(dev)          # |x| <= magnitude
+    out = ops.rowmlp_tc(ops.RowPairPack([(W, b)], [kin]), [(x, None, 1.0)])
+    ref = x.double() @ W.double().t() + b.double()
+    err = float((out.double() - ref).abs().max())
+    scale = float(ref.abs().max())
+    assert err <= 2e-6 * scale + 1e-7, f"max abs error {err:.3e} at output scale {scale:.3e}"
+
+
+@gpu
+def test_raw_input_range_check():
+    dev = torch.device("cuda")
+    ops.check_fp16_range(torch.full((4, 4), 2.9e4, device=dev), "x")
+    for bad in (torch.full((4, 4), 1.0e5, device=dev), torch.tensor([[float("nan")]], device=dev)):
+        with pytest.raises(RuntimeError, match="fp16x3"):
+            ops.check_fp16_range(bad, "x")

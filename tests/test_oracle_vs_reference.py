@@ -1,9 +1,9 @@
-"""Live pin (build container only): restatement and mesh-layout builders against the
-reference's own classes / transforms imported verbatim from /root/reference."""
+"""Live pin: restatement and mesh-layout builders against the reference's own classes / transforms imported verbatim
+(from /root/reference in the build container, from the staged byte-for-byte copy baseline/_ref elsewhere)."""
 import pytest
 import torch
 
-from conftest import rel_l2
+from conftest import rel_l2, shipped_model
 
 pytestmark = pytest.mark.reference
 
@@ -17,7 +17,7 @@ def gfd():
 def test_shipped_3s_checkpoint_one_step(gfd):
     from graphs4cfd_b200 import mesh as M
     from oracle import restate as R
-    model = gfd.nn.NsThreeScaleGNN(model="3S-GNN-NsCircle-v1")
+    model = shipped_model(gfd, "mus3")
     n = 2000
     g = M.build_mus_mesh(n, 6, M.auto_cells(n, 3), seed=3)
     ref = model.solve(g.clone(), 2)
@@ -28,7 +28,7 @@ def test_shipped_3s_checkpoint_one_step(gfd):
 def test_shipped_remus_checkpoint_one_step(gfd):
     from graphs4cfd_b200 import mesh as M
     from oracle import restate as R
-    model = gfd.nn.NsRotEquiTreeScaleGNN(model="RE3S-GNN-NsEllipse-v1")
+    model = shipped_model(gfd, "remus")
     g = M.build_remus_mesh(400, 5, seed=5, points="uniform")
     ref = model.solve(g.clone(), 2)
     out = R.solve({k: v.detach() for k, v in model.state_dict().items()}, g.clone(), 2)

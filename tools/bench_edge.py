@@ -82,7 +82,7 @@ if os.environ.get("G4C_PROFILE"):
     L.lib().g4c_debug_profile(vcode, buf.ctypes.data_as(C.c_void_p))        # drop warm-up + timing launches
     launch(variant)
     L.check(L.lib().g4c_debug_profile(vcode, buf.ctypes.data_as(C.c_void_p)))
-    print(f"phase profile of {variant} (the MMA issuer has no laps in v5):")
+    print(f"phase profile of {variant} (laps of lane 0 of one warp per role in CTA 0):")
     names = {0: ("epilogue warp 0", ["wait MMA (hidden)", "wait MMA (last)", "hidden epilogue", "last: statistics", "last: barrier", "last: normalise+agg+store", "unit end", "-"]),
              8: ("loader warp 16", ["wait rows", "wait acc release", "process + prefetch", "-", "-", "-", "-", "-"]),
              16: ("MMA issuer", ["wait loaders", "wait epilogue", "issue", "-", "-", "-", "-", "-"])}
