@@ -57,7 +57,7 @@ def parse():
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-parity", action="store_true", help="N > 1: skip the check against the single-GPU fp32 engine")
     ap.add_argument("--skip-gpu-eager", action="store_true")
-    ap.add_argument("--no-overlap", action="store_true", help="N > 1 (MuS): halo exchange in front of every block instead of behind its first kernel")
+    ap.add_argument("--overlap", action="store_true", help="N > 1 (MuS): halo exchange behind the first kernel of every block instead of in front of it")
     ap.add_argument("--rollout-check", type=int, default=0,
                     help="N > 1: additionally roll out this many steps and report rel-L2 against the single-GPU engine (configs[4])")
     return ap.parse_args()
@@ -279,7 +279,7 @@ def run_g4c(a):
         # node-range partition; REMuS-GNN gets the edge-halo variant (graphs4cfd_b200/partition_remus.py)
         from graphs4cfd_b200.partition import partitioned_rollout
         eng = partitioned_rollout(params, g, rank=rank, world=world, precision=a.precision, device=dev, cuda_graph=not a.no_graph,
-                                  overlap=not a.no_overlap)
+                                  overlap=a.overlap)
     else:
         eng = Rollout(params, g, precision=a.precision, device=dev, cuda_graph=not a.no_graph)
     N_local, nf, fw = eng.N, eng.nf, eng.field_width

@@ -155,6 +155,21 @@ def stream_ptr(device=None):
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+def cuda_device(device) -> torch.device:
+    """``device`` as a torch.device with an explicit index ("cuda" -> the current device's ordinal)."""
+    device = torch.device(device)
+    if device.type == "cuda" and device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    return device
+
+
+def graph_capture(graph: "torch.cuda.CUDAGraph", device: torch.device):
+    """``torch.cuda.graph`` on a capture stream that belongs to ``device``.  (torch.cuda.graph's default capture stream is
+    created once per process on whatever device was current at its first use; capturing another device's kernels on it
+    records an EMPTY graph — seen when an engine on cuda:1 was built before one on cuda:0.)"""
+    return torch.cuda.graph(graph, stream=torch.cuda.Stream(device=device))
+
+
 def launch(name, desc, *tensors):
     """Call the descriptor entry point ``name`` for tensors that must all live on ONE CUDA device: the kernel goes to that
     device's current stream with that device made current for the call (kernel attributes, tensor maps and the launch

@@ -22,18 +22,22 @@ def _swizzled_images(M: torch.Tensor):
 
 
 # tcgen05.mma adds every product into its fp32 accumulator with round-toward-zero: each accumulating MMA pulls the running sum
-# toward zero by a fraction of an ulp, a SYSTEMATIC relative shrink that grows with the number of MMAs of a GEMM (measured on
-# B200, tools/tc_bias.py / profiles/r2h_tc_bias.txt: -4.45e-7 for K = 128 = 24 MMAs of the 3-term split, the same for centred
-# and offset inputs; torch's fp32 matmul: -5e-10).  LayerNorm cancels a scale error, but encoders, decoders and hidden layers
-# have none, and a rollout integrates the bias step after step (drift linear in the step count instead of a random walk).
-# The kernels multiply the accumulator by 1/s anyway, so the expected shrink is folded into that factor: exact on average,
-# no instruction added.  kappa = relative shrink per accumulating MMA.
-TC_RZ_KAPPA = 4.45e-7 / 24.0
+# toward zero by a fraction of an ulp, a SYSTEMATIC relative shrink that grows with the number of MMAs of a GEMM.  Measured on
+# B200 (tools/tc_bias.py, profiles/r2h_tc_bias.txt; the same for centred and offset inputs; torch's fp32 matmul: -5e-10):
+#     3 MMAs (one K = 16 step of the 3-term split)  -0.9e-7      24 MMAs (K = 128)  -4.45e-7
+#     48 MMAs (K = 256)                             -8.26e-7     72 MMAs (K = 384)  -1.21e-6      i.e.  6.2e-8 + 1.594e-8 n
+# LayerNorm cancels a scale error, but encoders, decoders and hidden layers have none, and a rollout integrates the bias step
+# after step (drift linear in the step count instead of a random walk: 6.1e-7 per step with the trained 3S-GNN).  The kernels
+# multiply the accumulator by 1/s anyway, so the expected shrink is folded into that factor: exact on average, no instruction
+# added (bias after compensation < 1.2e-7 even through three layers; 100-step rollout drift 9.0e-5 -> 3.6e-5 at a noise floor of
+# 2.5e-5, profiles/r2h_rollout_drift.txt).
+TC_RZ_SHRINK = (6.2e-8, 1.594e-8)          # relative shrink of an accumulator = a + b * (number of MMAs it received)
 
 
 def rz_compensation(n_mma: int) -> float:
     """Factor that undoes the mean round-toward-zero shrink of an accumulator that received ``n_mma`` MMAs."""
-    return 1.0 + TC_RZ_KAPPA * n_mma
+    a, b = TC_RZ_SHRINK
+    return 1.0 + (a + b * n_mma if n_mma > 0 else 0.0)
 
 
 def weight_scale(W: torch.Tensor) -> float:

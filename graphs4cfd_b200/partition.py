@@ -23,6 +23,8 @@ from typing import Dict, List, Optional
 import numpy as np
 import torch
 
+from . import _lib as LIB
+
 from .program import block_program, hidden_width
 
 
@@ -452,12 +454,13 @@ class PartitionedRollout:
     """Rank-local slice of a MuS-GNN rollout.  API mirrors Rollout (solve / step_only / pred / node_in)."""
 
     def __init__(self, params, graph, rank: int, world: int, precision="auto", device="cuda", cuda_graph=False, renumber=True,
-                 overlap=True):
+                 overlap=False):
         """overlap: the halo exchange of a tensor-core message-passing block runs on NCCL's stream behind the block's first
-        kernel (the per-node products of the own rows) instead of in front of the block."""
+        kernel (the per-node products of the own rows) instead of in front of the block.  Off by default: measured on B200
+        (profiles/r2i_*, r2j_*) the extra launch for the ghost rows' products costs more than the hidden latency saves."""
         from . import ops
         self.overlap = overlap
-        self.device = torch.device(device)
+        self.device = LIB.cuda_device(device)
         self.rank, self.world, self.precision = rank, world, precision
         node_perm = None
         if renumber and graph.pos.shape[0] > 1:
@@ -532,7 +535,7 @@ class PartitionedRollout:
             self.launches_per_step = ops.L.launch_count() - n0 + 1          # libg4c kernels per step (+ step_update)
             torch.cuda.synchronize(self.device)
             self._graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self._graph):
+            with LIB.graph_capture(self._graph, self.device):
                 for fn in self._steps:
                     fn()
         self._graph.replay()

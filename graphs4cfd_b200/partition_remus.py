@@ -26,6 +26,8 @@ from typing import Dict, Optional
 import numpy as np
 import torch
 
+from . import _lib as LIB
+
 from .partition import Xchg, _by_owner, _np, strip_owners
 from .program import hidden_width
 
@@ -384,7 +386,7 @@ class PartitionedRemusRollout:
 
     def __init__(self, params, graph, rank: int, world: int, precision="auto", device="cuda", cuda_graph=False):
         from . import ops
-        self.device = dev = torch.device(device)
+        self.device = dev = LIB.cuda_device(device)
         self.rank, self.world, self.precision = rank, world, precision
         self.params = {k: v.to(dev) for k, v in params.items()}
         self.H = hidden_width(self.params)
@@ -460,7 +462,7 @@ class PartitionedRemusRollout:
             self.launches_per_step = ops.L.launch_count() - n0 + 1          # libg4c kernels per step (+ step_update)
             torch.cuda.synchronize(self.device)
             self._graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self._graph):
+            with LIB.graph_capture(self._graph, self.device):
                 for fn in self._steps:
                     fn()
         self._graph.replay()

@@ -16,6 +16,8 @@ from typing import Dict, List, Optional
 import numpy as np
 import torch
 
+from . import _lib as LIB
+
 from . import ops
 from .blocks import children_csr, pooled_edges
 from .program import block_program, hidden_width, is_remus
@@ -63,7 +65,7 @@ class Rollout:
         that gathered source rows are near in memory whatever order the mesh came in; inputs (``set_field``) and outputs
         (``solve``) stay in the caller's node order, ``node_in`` / ``pred`` / ``field0`` are in ENGINE order
         (``node_perm[i]`` = caller's index of engine row i)."""
-        self.device = torch.device(device)
+        self.device = LIB.cuda_device(device)
         if self.device.type != "cuda":
             raise RuntimeError("Rollout needs a CUDA device; graphs4cfd_b200 has no CPU path")
         self.params = {k: v.to(self.device) for k, v in _state_of(model_or_params).items()}
@@ -286,7 +288,7 @@ class Rollout:
             torch.cuda.current_stream(self.device).wait_stream(s)
             torch.cuda.synchronize(self.device)
             self._graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self._graph):
+            with LIB.graph_capture(self._graph, self.device):
                 self._run_step_eager()
         self._graph.replay()
 

@@ -140,3 +140,33 @@ def test_raw_input_range_check():
     for bad in (torch.full((4, 4), 1.0e5, device=dev), torch.tensor([[float("nan")]], device=dev)):
         with pytest.raises(RuntimeError, match="fp16x3"):
             ops.check_fp16_range(bad, "x")
+
+
+@gpu
+@pytest.mark.parametrize("segs", [[128], [128, 128], [128, 128, 128], [2, 128]])
+def test_round_toward_zero_shrink_is_compensated(segs):
+    """tcgen05.mma accumulates with round-toward-zero: uncompensated, a K = 128 GEMM comes out 4.45e-7 too small (a pure scale
+    error, measured in tools/tc_bias.py).  The packs fold the expected shrink into the accumulator scale: the remaining scale
+    error <err, ref> / <ref, ref> must stay below 1.5e-7 (fp32 granularity of the factor: 6e-8) and far below the uncompensated
+    value for the wide cases."""
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(5)
+    rows, K = 20000, sum(segs)
+    xs = [torch.randn(rows, w, generator=g).to(dev) for w in segs]
+    W = (torch.randn(128, K, generator=g) / K ** 0.5).to(dev)
+    b = (torch.randn(128, generator=g) * 0.1).to(dev)
+    ref = torch.cat(xs, 1).double() @ W.double().t() + b.double()
+
+    def bias(out):
+        err = out.double() - ref
+        return float((err * ref).sum() / (ref * ref).sum())
+
+    comp = bias(ops.rowmlp_tc(ops.RowPairPack([(W, b)], segs), [(t, None, 1.0) for t in xs]))
+    assert abs(comp) < 1.5e-7, comp
+    saved = ops.TC_RZ_SHRINK
+    try:
+        ops.TC_RZ_SHRINK = (0.0, 0.0)
+        raw = bias(ops.rowmlp_tc(ops.RowPairPack([(W, b)], segs), [(t, None, 1.0) for t in xs]))
+    finally:
+        ops.TC_RZ_SHRINK = saved
+    assert raw < -3e-7 and abs(comp) < 0.35 * abs(raw), (raw, comp)

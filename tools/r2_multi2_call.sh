@@ -7,6 +7,6 @@ run() { name=$1; shift
   timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29621 \
       bench.py --gpus 2 --steps 10 --warmup 3 "$@" > gpurun_out/r2i_${name}_n2.json 2> gpurun_out/r2i_${name}_n2.err; }
 run mus
-run mus_nooverlap --no-overlap --skip-parity
+run mus_overlap --overlap --skip-parity
 run remus --model remus
 cat gpurun_out/r2i_multi2_pytest.log; for f in gpurun_out/r2i_*_n2.json; do echo $f; head -c 700 $f; echo; done; tail -5 gpurun_out/r2i_*_n2.err

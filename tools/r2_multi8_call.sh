@@ -7,7 +7,7 @@ run() { name=$1; shift
   timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29631 \
       bench.py --gpus $N "$@" > gpurun_out/r2j_${name}_n$N.json 2> gpurun_out/r2j_${name}_n$N.err; }
 run mus --steps 20 --warmup 5
-run mus_nooverlap --steps 20 --warmup 5 --no-overlap --skip-parity
+run mus_overlap --steps 20 --warmup 5 --overlap --skip-parity
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29633 \
     tools/partition_timeline.py > gpurun_out/r2j_timeline_n$N.txt 2> gpurun_out/r2j_timeline_n$N.err
 run remus --model remus --steps 10 --warmup 3

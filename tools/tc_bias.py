@@ -14,8 +14,8 @@ import torch.nn.functional as F  # noqa: E402
 from graphs4cfd_b200 import ops  # noqa: E402
 
 if "--no-compensation" in sys.argv:
-    ops.TC_RZ_KAPPA = 0.0
-print(f"# TC_RZ_KAPPA = {ops.TC_RZ_KAPPA:.3e} per accumulating MMA")
+    ops.TC_RZ_SHRINK = (0.0, 0.0)
+print(f"# TC_RZ_SHRINK = {ops.TC_RZ_SHRINK} (relative shrink of an accumulator = a + b * number of MMAs)")
 
 dev = torch.device("cuda")
 g = torch.Generator().manual_seed(0)
