@@ -207,5 +207,41 @@ def main():
     print(f"total {total / 1e6:.2f} MB")
 
 
+def extra():
+    """Round-2 additions, written WITHOUT touching the fixtures above (own seeds): the remaining advection models
+    (nn/mus_gnn.py:68-97, 173-218, 984-1053) and the REMuS angle -> edge blocks with aggr='sum' (blocks.py:307-333)."""
+    torch.manual_seed(1234)
+    fx = {}
+
+    def model_fixture(cls, arch, g, n_out):
+        model = cls(arch=arch)
+        out = model.solve(g.clone(), n_out)
+        return dict(mesh=mesh_dict(g), params=sd(model), out=out, n_out=n_out, cls=cls.__name__)
+
+    for levels, cls, n, seed in ((1, gfd.nn.AdvOneScaleGNN, 500, 21), (2, gfd.nn.AdvTwoScaleGNN, 700, 22),
+                                 (4, gfd.nn.AdvFourScaleGNN, 1600, 24)):
+        ga = M.build_mus_mesh(n, 6, M.auto_cells(n, levels) if levels > 1 else (), seed=seed, num_fields=1)
+        del ga.glob
+        ga.loc = torch.randn(n, 2) * 0.3
+        fx[f"model_adv{levels}_h16"] = model_fixture(cls, mus_arch(16, levels, adv=True, nf=1, node_in=4), ga, 2)
+
+    Hs, k = 32, 5
+    g = M.build_remus_mesh(130, k, seed=4, points="uniform")
+    E1 = g.edge_index.size(1)
+    emp = B.EdgeMP((3 * Hs, (Hs, Hs), True), (2 * Hs, (Hs, Hs), True), aggr="sum").eval()
+    e1, a1 = torch.randn(E1, Hs), torch.randn(E1 * k, Hs)
+    with torch.no_grad():
+        e1o, a1o = emp(e1, a1, g.angle_index)
+    fx["remus_edgemp_sum_h32"] = dict(mesh=mesh_dict(g), k=k, params={"emp." + a: b for a, b in sd(emp).items()},
+                                      e1=e1, a1=a1, e1_out=e1o, a1_out=a1o)
+    for name, d in fx.items():
+        path = os.path.join(OUT, name + ".pt")
+        torch.save(d, path)
+        print(f"{name:28s} {os.path.getsize(path) / 1e6:7.2f} MB")
+
+
 if __name__ == "__main__":
-    main()
+    if "--extra" in sys.argv:
+        extra()
+    else:
+        main()

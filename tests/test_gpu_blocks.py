@@ -68,7 +68,8 @@ def test_down_up():
     assert rel_l2(g.field.cpu(), d["field_h_up"]) <= TOL_BLOCK
 
 
-@pytest.mark.parametrize("name", ["model_ns1_h16", "model_ns2_h16", "model_ns3_h32", "model_ns4_h16", "model_adv3_h16"])
+@pytest.mark.parametrize("name", ["model_ns1_h16", "model_ns2_h16", "model_ns3_h32", "model_ns4_h16", "model_adv1_h16", "model_adv2_h16",
+                                  "model_adv3_h16", "model_adv4_h16"])
 @pytest.mark.parametrize("cuda_graph", [False, True])
 def test_mus_rollout_golden(name, cuda_graph):
     import graphs4cfd_b200 as g4

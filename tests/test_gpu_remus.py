@@ -43,6 +43,18 @@ def test_remus_blocks_golden():
         assert rel_l2(nv.cpu(), d["node_vec"]) <= TOL_BLOCK
 
 
+def test_remus_edgemp_sum_golden():
+    """EdgeMP(aggr='sum') (blocks.py:307-333): fixture written by the unmodified reference."""
+    import graphs4cfd_b200 as g4
+    d = load_golden("remus_edgemp_sum_h32")
+    H = 32
+    g = mesh_from(d["mesh"]).to("cuda")
+    emp = load_into(g4.EdgeMP((3 * H, (H, H), True), (2 * H, (H, H), True), aggr="sum"), d["params"], "emp")
+    with torch.no_grad():
+        e1o, a1o = emp(dev(d["e1"]), dev(d["a1"]), g.angle_index)
+    assert rel_l2(e1o.cpu(), d["e1_out"]) <= TOL_BLOCK and rel_l2(a1o.cpu(), d["a1_out"]) <= TOL_BLOCK
+
+
 @pytest.mark.parametrize("cuda_graph", [False, True])
 def test_remus_rollout_golden(cuda_graph):
     import graphs4cfd_b200 as g4

@@ -48,8 +48,8 @@ def test_remus_blocks():
     assert rel_l2(R.edge_scalar_to_node_vector(d["e1"], g.edgeUnitVectorInverse), d["node_vec"]) <= TOL
 
 
-@pytest.mark.parametrize("name", ["model_ns1_h16", "model_ns2_h16", "model_ns3_h32", "model_ns4_h16",
-                                  "model_adv3_h16", "model_remus_h32"])
+@pytest.mark.parametrize("name", ["model_ns1_h16", "model_ns2_h16", "model_ns3_h32", "model_ns4_h16", "model_adv1_h16",
+                                  "model_adv2_h16", "model_adv3_h16", "model_adv4_h16", "model_remus_h32"])
 def test_model_rollout(name):
     d = load_golden(name)
     out = R.solve(d["params"], mesh_from(d["mesh"]), d["n_out"])
@@ -62,3 +62,11 @@ def test_program_derivation():
     kinds = [k for _, k in R.block_program(d["params"])]
     assert kinds == ["mlp", "mlp"] + ["mp"] * 4 + ["down"] + ["mp"] * 2 + ["down"] + ["mp"] * 4 + ["up"] + ["mp"] * 2 \
         + ["up"] + ["mp"] * 4 + ["mlp"]
+
+
+def test_remus_edgemp_sum():
+    """EdgeMP with aggr='sum' (blocks.py:307-333) against the fixture the unmodified reference wrote."""
+    d = load_golden("remus_edgemp_sum_h32")
+    g = mesh_from(d["mesh"])
+    e1o, a1o = R.edge_mp(d["params"], "emp", d["e1"], d["a1"], g.angle_index, "sum")
+    assert rel_l2(e1o, d["e1_out"]) <= TOL and rel_l2(a1o, d["a1_out"]) <= TOL
