@@ -88,6 +88,13 @@ class StepUpdateDesc(C.Structure):
                 ("node_in", _f32p), ("outputs", _f32p)]
 
 
+class KnnDesc(C.Structure):
+    _fields_ = [("n_points", C.c_int64), ("n_queries", C.c_int64), ("k", C.c_int32), ("exclude_self", C.c_int32),
+                ("pos", _f32p), ("query", _f32p), ("cell_start", _i32p), ("sorted_idx", _i32p),
+                ("x0", C.c_float), ("y0", C.c_float), ("cell", C.c_float), ("gx", C.c_int32), ("gy", C.c_int32),
+                ("_pad", C.c_int32), ("nbr", _i32p)]
+
+
 class HaloDesc(C.Structure):
     _fields_ = [("n_rows", C.c_int64), ("width", C.c_int32), ("_pad", C.c_int32), ("idx", _i32p),
                 ("src", _f32p), ("dst", _f32p)]
@@ -109,6 +116,7 @@ EXPORTS = {
     "g4c_step_update": (C.c_int, [C.POINTER(StepUpdateDesc), C.c_void_p]),
     "g4c_halo_pack": (C.c_int, [C.POINTER(HaloDesc), C.c_void_p]),
     "g4c_halo_unpack": (C.c_int, [C.POINTER(HaloDesc), C.c_void_p]),
+    "g4c_plan_knn": (C.c_int, [C.POINTER(KnnDesc), C.c_void_p]),
     "g4c_host_guillard": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
     "g4c_debug_profile": (C.c_int, [C.c_int32, C.c_void_p]),
     "g4c_debug_tma": (C.c_int, [C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),

@@ -40,6 +40,7 @@ int edge_to_node_launch(const G4cEdgeToNodeDesc& d, cudaStream_t st);
 int interp_launch(const G4cInterpDesc& d, cudaStream_t st);
 int step_update_launch(const G4cStepUpdateDesc& d, cudaStream_t st);
 int halo_launch(const G4cHaloDesc& d, cudaStream_t st, bool pack);
+int knn_launch(const G4cKnnDesc& d, cudaStream_t st);
 int tc2_test_launch(int test, const float* A, const void* Wpack, float inv_scale, const float* P, float* D, int flags, cudaStream_t st);
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -204,6 +205,15 @@ int g4c_halo_pack(const G4cHaloDesc* d, void* stream) {
 int g4c_halo_unpack(const G4cHaloDesc* d, void* stream) {
     if (!d || !d->idx || !d->src || !d->dst || (d->width & 3)) { set_error("g4c_halo_unpack: bad descriptor"); return G4C_EINVAL; }
     return halo_launch(*d, static_cast<cudaStream_t>(stream), false);
+}
+
+int g4c_plan_knn(const G4cKnnDesc* d, void* stream) {
+    if (!d || !d->pos || !d->query || !d->cell_start || !d->sorted_idx || !d->nbr || d->n_points < 0 || d->n_queries < 0) {
+        set_error("g4c_plan_knn: bad descriptor"); return G4C_EINVAL; }
+    if (d->k < 1 || d->k > 16) { set_error("g4c_plan_knn: k=%d (1..16)", d->k); return G4C_EUNSUPPORTED; }
+    if (d->gx < 1 || d->gy < 1 || !(d->cell > 0.f)) { set_error("g4c_plan_knn: bad grid"); return G4C_EINVAL; }
+    if (d->n_points > 0x7fffffffLL || d->n_queries > 0x7fffffffLL) { set_error("g4c_plan_knn: int32 index range exceeded"); return G4C_EUNSUPPORTED; }
+    return knn_launch(*d, static_cast<cudaStream_t>(stream));
 }
 
 int g4c_debug_tc2(int32_t test, const float* A, const void* W_pack, float w_inv_scale, const float* P, float* D, int32_t flags, void* stream) {

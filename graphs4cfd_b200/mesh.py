@@ -131,7 +131,15 @@ def uniform_points(n: int, seed: int = 0, box=(1.0, 1.0)) -> torch.Tensor:
 # ----------------------------------------------------------------------------- kNN
 def knn_edges(pos: torch.Tensor, k: int):
     """(edge_index int64[2, N*k], edge_attr fp32[N*k, 2]); edge j*k+m points from the
-    m-th nearest neighbour of node j to node j (all in-edges of a node are contiguous)."""
+    m-th nearest neighbour of node j to node j (all in-edges of a node are contiguous).
+    CUDA positions: the search runs on the device (g4c_plan_knn); host positions: scipy's k-d tree."""
+    if pos.is_cuda:
+        from . import ops
+        n = pos.shape[0]
+        nbr = ops.knn(pos.contiguous(), None, k)
+        centre = torch.arange(n, device=pos.device).repeat_interleave(k)
+        edge_index = torch.stack([nbr.reshape(-1), centre])
+        return edge_index, pos[edge_index[1]] - pos[edge_index[0]]
     from scipy.spatial import cKDTree
     pts = pos.double().numpy()
     n = pts.shape[0]
@@ -150,6 +158,12 @@ def knn_edges(pos: torch.Tensor, k: int):
 
 def knn_interp_weights(pos_x: torch.Tensor, pos_y: torch.Tensor, k: int):
     """for every y its k nearest x: (y_idx, x_idx, 1/max(d^2,1e-16))."""
+    if pos_x.is_cuda:
+        from . import ops
+        x_idx = ops.knn(pos_x.contiguous(), pos_y.contiguous(), k).reshape(-1)
+        y_idx = torch.arange(pos_y.size(0), device=pos_y.device).repeat_interleave(k)
+        diff = pos_x[x_idx] - pos_y[y_idx]
+        return y_idx, x_idx, 1.0 / torch.clamp((diff * diff).sum(dim=-1, keepdim=True), min=1e-16)
     from scipy.spatial import cKDTree
     _, nbr = cKDTree(pos_x.double().numpy()).query(pos_y.double().numpy(), k=k, workers=-1)
     nbr = np.asarray(nbr, dtype=np.int64).reshape(pos_y.size(0), k)
@@ -167,14 +181,14 @@ def grid_clustering(pos_1: torch.Tensor, cell_size: float):
     p = pos_1
     start = p.min(dim=0).values
     end = p.max(dim=0).values
-    size = torch.tensor([cell_size, cell_size], dtype=p.dtype)
+    size = torch.tensor([cell_size, cell_size], dtype=p.dtype, device=p.device)
     num_voxels = ((end - start) / size).to(torch.long) + 1
     coord = ((p - start) / size).to(torch.long)
     cluster = coord[:, 0] + coord[:, 1] * num_voxels[0]
     mask, inverse = torch.unique(cluster, sorted=True, return_inverse=True)
     n2 = mask.numel()
-    summed = torch.zeros(n2, 2, dtype=p.dtype).index_add_(0, inverse, p)
-    count = torch.zeros(n2, dtype=p.dtype).index_add_(0, inverse, torch.ones(p.size(0), dtype=p.dtype))
+    summed = torch.zeros(n2, 2, dtype=p.dtype, device=p.device).index_add_(0, inverse, p)
+    count = torch.zeros(n2, dtype=p.dtype, device=p.device).index_add_(0, inverse, torch.ones(p.size(0), dtype=p.dtype, device=p.device))
     pos_2 = summed / count.clamp(min=1).unsqueeze(1)
     e_12 = (pos_2[inverse] - p) / cell_size
     return pos_2, cluster, mask, inverse, e_12
@@ -185,17 +199,18 @@ def guillard_coarsening(edge_index: torch.Tensor, num_nodes: int) -> torch.Tenso
     """Sequential node-nested coarsening: visiting nodes in order, a node still marked
     coarse removes its k senders from the coarse set."""
     k = int((edge_index[1] == 0).sum())
-    senders = edge_index[0].view(-1, k).numpy()
+    dev = edge_index.device                    # the sweep is sequential: it runs on the host whatever the device of the mesh
+    senders = edge_index[0].view(-1, k).cpu().numpy()
     # Host-side work either way (mesh synthesis for tests and the benchmark, not the product path): the C helper of libg4c
     # when the library has been built, the same sweep in Python when it has not (e.g. oracle-only test runs).
     from . import _lib
     if os.path.exists(_lib.LIB_PATH):
-        return torch.from_numpy(_lib.host_guillard(senders, int(num_nodes)))
+        return torch.from_numpy(_lib.host_guillard(senders, int(num_nodes))).to(dev)
     coarse = np.ones(int(num_nodes), dtype=bool)
     for i in range(senders.shape[0]):
         if coarse[i]:
             coarse[senders[i]] = False
-    return torch.from_numpy(coarse)
+    return torch.from_numpy(coarse).to(dev)
 
 
 def _local_index(edge_index: torch.Tensor):
@@ -214,8 +229,9 @@ def extend_graph(edge_index: torch.Tensor, edge_attr: torch.Tensor, k: int):
     local, _, _ = _local_index(edge_index)
     size = edge_attr.norm(2, dim=1, keepdim=True)
     unit = edge_attr / size
-    row = (local[0].unsqueeze(1) * k + torch.arange(k)).reshape(-1)
-    col = torch.arange(num_edges).repeat_interleave(k)
+    dev = edge_index.device
+    row = (local[0].unsqueeze(1) * k + torch.arange(k, device=dev)).reshape(-1)
+    col = torch.arange(num_edges, device=dev).repeat_interleave(k)
     cos = (unit[row] * unit[col]).sum(dim=1)
     sin = unit[row, 0] * unit[col, 1] - unit[row, 1] * unit[col, 0]
     angle_attr = torch.cat([size[row], size[col], cos.unsqueeze(1), sin.unsqueeze(1)], dim=1)
@@ -228,7 +244,7 @@ def angle_index_down(edge_index1, edge_attr1, edge_index2, edge_attr2, coarse_in
     local1, owners1, _ = _local_index(edge_index1)
     # position of each coarse node among the level-1 targets -> its k in-edges
     pos_in_l1 = torch.searchsorted(owners1, coarse_index2)
-    in_edges = pos_in_l1.unsqueeze(1) * k + torch.arange(k)                      # [V2, k]
+    in_edges = pos_in_l1.unsqueeze(1) * k + torch.arange(k, device=edge_index1.device)                      # [V2, k]
     # level-2 edges grouped by source node, ascending node then ascending edge id
     src2 = torch.searchsorted(coarse_index2, edge_index2[0])
     order = torch.sort(src2, stable=True).indices                                # out_edges_index2
@@ -265,16 +281,20 @@ def _omega(pos: torch.Tensor):
 
 def build_mus_mesh(n: int, k: int = 6, cells: Sequence[float] = (), seed: int = 0,
                    points: str = "jittered", num_fields: int = 3, edge_scale=None,
-                   glob: float = 0.3) -> Mesh:
+                   glob: float = 0.3, device=None) -> Mesh:
     """MuS-GNN input: level-1 kNN graph + ``len(cells)`` grid-clustered levels.
     ``cells`` in units of the mean edge length when given as ("auto", ratio...) is not
-    supported; pass absolute sizes (see ``auto_cells``)."""
+    supported; pass absolute sizes (see ``auto_cells``).
+    ``device``: build on that CUDA device (kNN by g4c_plan_knn, everything else torch device ops); the same points give
+    the same index arrays as the host build (tests/test_gpu_plan.py)."""
     pos = jittered_points(n, seed) if points == "jittered" else uniform_points(n, seed)
+    if device is not None:
+        pos = pos.to(device)
     edge_index, edge_attr = knn_edges(pos, k)
     r = float(edge_attr.norm(dim=1).mean()) if edge_scale is None else edge_scale
     edge_attr = edge_attr / (2 * r)
     m = Mesh(pos=pos, edge_index=edge_index, edge_attr=edge_attr,
-             field=_fields(pos, num_fields), glob=torch.full((n, 1), glob), omega=_omega(pos))
+             field=_fields(pos, num_fields), glob=torch.full((n, 1), glob, device=pos.device), omega=_omega(pos))
     p = pos
     for lvl, cell in enumerate(cells, start=2):
         pos_l, cluster, mask, idx, e = grid_clustering(p, cell)
@@ -294,12 +314,15 @@ def auto_cells(n: int, levels: int, box=(4.0, 1.0), ratios=(5.0, 20.0, 80.0)):
 
 
 def build_remus_mesh(n: int, k: int = 6, seed: int = 0, points: str = "jittered",
-                     interp_k: int = None, edge_scale=(None, None, None)) -> Mesh:
+                     interp_k: int = None, edge_scale=(None, None, None), device=None) -> Mesh:
     """REMuS-GNN 3-level input in the layouts of transforms/remus.py:93-147 +
-    transforms/interpolate.py:147-155."""
+    transforms/interpolate.py:147-155.  ``device``: build on that CUDA device (kNN searches by g4c_plan_knn, the closed-form
+    angle lists as torch device ops; only the sequential Guillard sweep visits the host)."""
     interp_k = k if interp_k is None else interp_k
     pos = jittered_points(n, seed) if points == "jittered" else uniform_points(n, seed)
-    m = Mesh(pos=pos, field=_fields(pos, 2), glob=torch.full((n, 1), 0.3), omega=_omega(pos))
+    if device is not None:
+        pos = pos.to(device)
+    m = Mesh(pos=pos, field=_fields(pos, 2), glob=torch.full((n, 1), 0.3, device=pos.device), omega=_omega(pos))
 
     def scaled(ei, ea, s):
         r = float(ea.norm(dim=1).mean()) if s is None else s

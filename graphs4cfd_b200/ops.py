@@ -544,6 +544,38 @@ def _pack_weight_single(W: torch.Tensor):
     return pack.view(torch.uint8).reshape(-1), 1.0 / s
 
 
+def knn(pos: torch.Tensor, query: Optional[torch.Tensor], k: int, points_per_cell: float = 3.0) -> torch.Tensor:
+    """g4c_plan_knn: the k nearest data points of every query, ascending distance, [n_queries, k] int64.  ``query=None``: the
+    kNN graph of ``pos`` itself (a point is not its own neighbour).  Same result as the host k-d tree (mesh.knn_edges /
+    knn_interp_weights; transforms/connect.py:58, transforms/interpolate.py:125).  Device tensors in, device tensor out."""
+    L.require_cuda_f32(pos, query)
+    self_graph = query is None
+    q = pos if self_graph else query
+    n, m = int(pos.shape[0]), int(q.shape[0])
+    both = pos if self_graph else torch.cat([pos, q], dim=0)
+    lo, hi = both.min(dim=0).values, both.max(dim=0).values
+    ext = (hi - lo).clamp(min=1e-20)
+    # the descriptor carries the cell size as fp32: bin the points with exactly that value
+    cell = float(torch.sqrt(ext[0] * ext[1] * points_per_cell / max(n, 1)).clamp(min=1e-20).float())
+    gx, gy = int(float(ext[0]) / cell) + 1, int(float(ext[1]) / cell) + 1
+    x0, y0 = float(lo[0]), float(lo[1])
+    # cell ids with the kernel's own arithmetic (double), points grouped by cell with ascending id inside a cell
+    cx = ((pos[:, 0].double() - x0) / cell).floor().clamp_(0, gx - 1).long()
+    cy = ((pos[:, 1].double() - y0) / cell).floor().clamp_(0, gy - 1).long()
+    cid = cy * gx + cx
+    order = torch.sort(cid, stable=True).indices
+    start = torch.zeros(gx * gy + 1, dtype=torch.int64, device=pos.device)
+    start[1:] = torch.bincount(cid, minlength=gx * gy).cumsum(0)
+    d = L.KnnDesc()
+    d.n_points, d.n_queries, d.k, d.exclude_self = n, m, int(k), int(self_graph)
+    sorted_idx, cell_start = order.to(torch.int32).contiguous(), start.to(torch.int32).contiguous()
+    nbr = torch.empty(m, k, dtype=torch.int32, device=pos.device)
+    d.pos, d.query, d.cell_start, d.sorted_idx, d.nbr = pos.data_ptr(), q.data_ptr(), cell_start.data_ptr(), sorted_idx.data_ptr(), nbr.data_ptr()
+    d.x0, d.y0, d.cell, d.gx, d.gy = x0, y0, cell, gx, gy
+    L.launch("g4c_plan_knn", d, pos, q, nbr)
+    return nbr.long()
+
+
 def debug_tc2(test: int, A: torch.Tensor, W: torch.Tensor, P: Optional[torch.Tensor] = None, flags: int = 0) -> torch.Tensor:
     """Self tests of the TMEM-operand / tcgen05.cp / CTA-pair primitives (csrc/tc2_test.cu)."""
     L.require_cuda_f32(A, W, P)

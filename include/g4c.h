@@ -265,6 +265,25 @@ typedef struct {
     int32_t dual, _pad2;
 } G4cRowTcDesc;
 
+/* Plan-time graph building on the device: exact 2-D k-nearest neighbours on a uniform cell grid.
+ * Replaces: torch_cluster.knn_graph behind connect_knn (transforms/connect.py:58: k in-edges per node, neighbour -> centre,
+ * ascending distance) and torch_cluster.knn behind get_knn_interpolate_weights (transforms/interpolate.py:125).
+ * The caller sorts the data points by cell id (cell = floor((p - origin) / cell), id = cy * gx + cx) and passes the prefix
+ * array; nbr[q, j] = index of the j-th nearest data point of query q (ascending distance, ties to the lower index; -1 when
+ * fewer than k points exist).  exclude_self: query q IS data point q and must not be its own neighbour (knn_graph, loop=False). */
+typedef struct {
+    int64_t n_points, n_queries;
+    int32_t k;                        /* 1..16                                                */
+    int32_t exclude_self;
+    const float* pos;                 /* [n_points, 2]                                        */
+    const float* query;               /* [n_queries, 2]                                       */
+    const int32_t* cell_start;        /* [gx*gy + 1]                                          */
+    const int32_t* sorted_idx;        /* [n_points] point ids grouped by cell, ascending id   */
+    float x0, y0, cell;               /* grid origin and cell size                            */
+    int32_t gx, gy, _pad;
+    int32_t* nbr;                     /* [n_queries, k] out                                   */
+} G4cKnnDesc;
+
 G4C_API int g4c_version(void);
 G4C_API const char* g4c_last_error(void);
 
@@ -279,6 +298,7 @@ G4C_API int g4c_interp_fwd(const G4cInterpDesc* d, void* stream);
 G4C_API int g4c_step_update(const G4cStepUpdateDesc* d, void* stream);
 G4C_API int g4c_halo_pack(const G4cHaloDesc* d, void* stream);
 G4C_API int g4c_halo_unpack(const G4cHaloDesc* d, void* stream);
+G4C_API int g4c_plan_knn(const G4cKnnDesc* d, void* stream);
 
 /* number of kernels this library has launched since load (bench.py reports it as gpu_launches) */
 G4C_API int64_t g4c_launch_count(void);

@@ -1,31 +1,70 @@
-"""Scratch: per-launch-group durations of one MuS-3 rollout step at 1M nodes, in sequence (CUDA events, eager launches)."""
-import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import torch
-from graphs4cfd_b200 import Rollout, ops
-from graphs4cfd_b200 import mesh as M
-from graphs4cfd_b200.archs import init_params, mus_arch
+"""Per-operation device time of one single-GPU rollout step (eager, CUDA events between the plan's operations), the N = 1
+companion of tools/partition_timeline.py.     python tools/step_timeline.py [--model mus|remus] [--nodes 1000000] [--reps 5]"""
+import argparse
+import collections
+import os
+import sys
 
-n = 1_000_000
-g = M.build_mus_mesh(n, 6, M.auto_cells(n, 3), seed=0)
-eng = Rollout(init_params(mus_arch(128, 3), seed=0), g, cuda_graph=False)
-for _ in range(3):
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--model", default="mus", choices=["mus", "remus"])
+ap.add_argument("--nodes", type=int, default=1_000_000)
+ap.add_argument("--hidden", type=int, default=128)
+ap.add_argument("--reps", type=int, default=5)
+a = ap.parse_args()
+
+from graphs4cfd_b200 import Rollout, ops  # noqa: E402
+from graphs4cfd_b200 import mesh as M  # noqa: E402
+from graphs4cfd_b200.archs import init_params, mus_arch, remus_arch  # noqa: E402
+
+dev = torch.device("cuda")
+if a.model == "remus":
+    g, params = M.build_remus_mesh(a.nodes, 6, seed=0), init_params(remus_arch(a.hidden), seed=0)
+else:
+    g, params = M.build_mus_mesh(a.nodes, 6, M.auto_cells(a.nodes, 3), seed=0), init_params(mus_arch(a.hidden, 3), seed=0)
+eng = Rollout(params, g, device=dev, cuda_graph=False)
+
+
+def label(op, s):
+    if op == "mp":
+        t = s["topo"]
+        return f"mp targets={t.n_targets} edges={t.n_edges} {'fixed-k' if t.fixed_k else 'csr'} e_out={'yes' if s['e_out'] is not None else 'no'}"
+    if op == "rowmlp":
+        return f"rowmlp rows={s.get('rows') or s['segs'][0][0].shape[0]} segs={[int(x[0].shape[1]) for x in s['segs']]} out={s['pack'].out_width}"
+    if op == "seg":
+        return f"seg_reduce groups={s['n']} rows={int(s['idx'].numel())}"
+    return op
+
+
+def run_one(op, s):
+    saved = eng.steps
+    eng.steps = [(op, s)]
+    eng._run_step_eager()
+    eng.steps = saved
+
+
+for _ in range(2):
     eng._run_step_eager()
 torch.cuda.synchronize()
-evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(eng.steps) + 1)]
-tot = {}
-for rep in range(5):
-    evs[0].record()
-    for i, (op, a) in enumerate(eng.steps):
-        eng.steps, saved = [eng.steps[i]], eng.steps
-        eng._run_step_eager()
-        eng.steps = saved
-        evs[i + 1].record()
+n = len(eng.steps)
+acc = [0.0] * n
+for _ in range(a.reps):
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+    ev[0].record()
+    for i, (op, s) in enumerate(eng.steps):
+        run_one(op, s)
+        ev[i + 1].record()
     torch.cuda.synchronize()
-    for i, (op, a) in enumerate(eng.steps):
-        rows = a["topo"].n_targets if op == "mp" else (a["out"].shape[0] if "out" in a else 0)
-        key = (i, op, rows)
-        tot[key] = tot.get(key, 0.0) + evs[i].elapsed_time(evs[i + 1]) / 5
-print(f"sum = {sum(tot.values()):.2f} ms")
-for (i, op, rows), ms in tot.items():
-    print(f"{i:3d} {op:7s} rows={rows:8d} {ms:7.3f} ms")
+    for i in range(n):
+        acc[i] += ev[i].elapsed_time(ev[i + 1]) / a.reps
+print(f"# single-GPU {a.model} step, {a.nodes} nodes, hidden {a.hidden}, eager, {a.reps} steps averaged; total {sum(acc):.3f} ms")
+by = collections.defaultdict(float)
+for (op, s), t in zip(eng.steps, acc):
+    lab = label(op, s)
+    by[lab] += t
+    print(f"{t:8.3f} ms  {lab}")
+print("# by operation shape:")
+for lab, t in sorted(by.items(), key=lambda kv: -kv[1]):
+    print(f"#   {t:8.3f} ms  {100 * t / sum(acc):5.1f} %  {lab}")
