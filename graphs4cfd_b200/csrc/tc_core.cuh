@@ -1,7 +1,6 @@
-// tc_core.cuh — Blackwell (sm_100a) primitives for the tensor-core path: mbarrier, bulk async copy
-// (TMA engine, 1-D), TMEM allocation, tcgen05.mma / commit / ld, UMMA descriptors, and the fp32 ->
-// (hi, lo) fp16 operand split written straight into the 128B-swizzled K-major shared-memory image
-// that tcgen05.mma reads.
+// tc_core.cuh — Blackwell (sm_100a) primitives shared by the tensor-core kernels: mbarrier, bulk async copy
+// (TMA engine, 1-D), tcgen05 fences and TMEM loads, UMMA shared-memory descriptors, and the fp32 -> (hi, lo) fp16
+// operand split.  (CTA-pair MMA issue, TMEM management and tcgen05.st live in tc2_core.cuh.)
 //
 // Operand image ("K-block"): 128 rows x 64 fp16 (128 B per row), rows packed at 128 B pitch, the eight
 // 16-byte chunks of row r stored at chunk position (c ^ (r & 7)).  This is the canonical
@@ -14,10 +13,6 @@
 
 namespace g4c {
 namespace tc {
-
-constexpr int kBlockBytes = 128 * 128;          // one K-block image: 128 rows x 128 B
-constexpr uint32_t kIdescF16_M128_N128 =        // kind::f16: D=f32, A=B=f16, K-major both, N=128, M=128
-    (1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -61,15 +56,6 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ------------------------------------------------------------------ TMEM
-__device__ __forceinline__ void tmem_alloc(uint32_t* smem_holder, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_holder)), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tmem_relinquish() {
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -84,21 +70,6 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;                               // layout: SWIZZLE_128B
     return d;
 }
-// D[tmem] (+)= A[smem] * B[smem]^T, one 128x128x16 fp16 MMA issued by the calling thread
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// arrive on `bar` when every previously issued tcgen05.mma of this thread has completed
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
 // 32 consecutive fp32 columns of this thread's TMEM lane (warp w reads lanes 32*(w%4) .. +31)
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     uint32_t r[32];
@@ -123,38 +94,6 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
     const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
     hi = *reinterpret_cast<const uint32_t*>(&h);
     lo = *reinterpret_cast<const uint32_t*>(&l);
-}
-
-// byte offset of element (row r, k) inside an operand made of consecutive K-blocks
-__device__ __forceinline__ uint32_t sw128_offset(int r, int k) {
-    const int kb = k >> 6, kk = k & 63;
-    return (uint32_t)kb * kBlockBytes + (uint32_t)r * 128 + (uint32_t)(((kk >> 3) ^ (r & 7)) << 4) + (uint32_t)((kk & 7) << 1);
-}
-
-// store 8 consecutive k (k0 % 8 == 0) of row r: one 16-byte chunk each into the hi and lo images
-__device__ __forceinline__ void store_split8(uint8_t* hi_img, uint8_t* lo_img, int r, int k0, const float (&x)[8]) {
-    uint4 h, l;
-    split2(x[0], x[1], h.x, l.x);
-    split2(x[2], x[3], h.y, l.y);
-    split2(x[4], x[5], h.z, l.z);
-    split2(x[6], x[7], h.w, l.w);
-    const uint32_t off = sw128_offset(r, k0);
-    *reinterpret_cast<uint4*>(hi_img + off) = h;
-    *reinterpret_cast<uint4*>(lo_img + off) = l;
-}
-
-// Issue the 3-term split product for one K-block (64 k): D += Ah*Wh + Al*Wh + Ah*Wl  (12 MMAs).
-// a_hi/a_lo/w_hi/w_lo are shared-memory byte addresses of the K-block images.
-__device__ __forceinline__ void issue_kblock_x3(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t w_hi, uint32_t w_lo,
-                                                bool first) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const uint64_t ah = make_desc_sw128(a_hi + j * 32), al = make_desc_sw128(a_lo + j * 32);
-        const uint64_t wh = make_desc_sw128(w_hi + j * 32), wl = make_desc_sw128(w_lo + j * 32);
-        umma_f16(d_tmem, ah, wh, kIdescF16_M128_N128, (first && j == 0) ? 0u : 1u);
-        umma_f16(d_tmem, al, wh, kIdescF16_M128_N128, 1u);
-        umma_f16(d_tmem, ah, wl, kIdescF16_M128_N128, 1u);
-    }
 }
 
 }  // namespace tc
