@@ -57,6 +57,8 @@ def parse():
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-parity", action="store_true", help="N > 1: skip the check against the single-GPU fp32 engine")
     ap.add_argument("--skip-gpu-eager", action="store_true")
+    ap.add_argument("--halo", default="auto", choices=["auto", "nccl", "p2p"],
+                    help="N > 1 (MuS): halo transport: NCCL all_to_all_single, or one kernel over NVLink peer memory (g4c_halo_put)")
     ap.add_argument("--overlap", action="store_true", help="N > 1 (MuS): halo exchange behind the first kernel of every block instead of in front of it")
     ap.add_argument("--rollout-check", type=int, default=0,
                     help="N > 1: additionally roll out this many steps and report rel-L2 against the single-GPU engine (configs[4])")
@@ -279,7 +281,7 @@ def run_g4c(a):
         # node-range partition; REMuS-GNN gets the edge-halo variant (graphs4cfd_b200/partition_remus.py)
         from graphs4cfd_b200.partition import partitioned_rollout
         eng = partitioned_rollout(params, g, rank=rank, world=world, precision=a.precision, device=dev, cuda_graph=not a.no_graph,
-                                  overlap=a.overlap)
+                                  overlap=a.overlap, halo=a.halo)
     else:
         eng = Rollout(params, g, precision=a.precision, device=dev, cuda_graph=not a.no_graph)
     N_local, nf, fw = eng.N, eng.nf, eng.field_width
@@ -383,6 +385,7 @@ def run_g4c(a):
         if world > 1 and hasattr(eng, "exchanges_per_step"):
             line["config"]["halo_exchanges_per_step"] = int(eng.exchanges_per_step)
             line["config"]["halo_overlap"] = bool(getattr(eng, "overlap", False))
+            line["config"]["halo_transport"] = getattr(eng, "halo", "nccl")
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:

@@ -88,6 +88,16 @@ class StepUpdateDesc(C.Structure):
                 ("node_in", _f32p), ("outputs", _f32p)]
 
 
+MAX_PEERS = 8
+
+
+class HaloPutDesc(C.Structure):
+    _fields_ = [("n_rows", C.c_int64), ("width", C.c_int32), ("n_peers", C.c_int32), ("src", _f32p), ("send_idx", _i32p),
+                ("seg_start", C.c_int32 * (MAX_PEERS + 1)), ("_pad", C.c_int32), ("dst", C.c_void_p * MAX_PEERS),
+                ("peer_flag", C.c_void_p * MAX_PEERS), ("my_flag", C.c_void_p * MAX_PEERS), ("state", C.c_void_p),
+                ("mail_stride", C.c_int64), ("mail", _f32p), ("ghost", _f32p), ("n_recv", C.c_int64)]
+
+
 class KnnDesc(C.Structure):
     _fields_ = [("n_points", C.c_int64), ("n_queries", C.c_int64), ("k", C.c_int32), ("exclude_self", C.c_int32),
                 ("pos", _f32p), ("query", _f32p), ("cell_start", _i32p), ("sorted_idx", _i32p),
@@ -116,6 +126,7 @@ EXPORTS = {
     "g4c_step_update": (C.c_int, [C.POINTER(StepUpdateDesc), C.c_void_p]),
     "g4c_halo_pack": (C.c_int, [C.POINTER(HaloDesc), C.c_void_p]),
     "g4c_halo_unpack": (C.c_int, [C.POINTER(HaloDesc), C.c_void_p]),
+    "g4c_halo_put": (C.c_int, [C.POINTER(HaloPutDesc), C.c_void_p]),
     "g4c_plan_knn": (C.c_int, [C.POINTER(KnnDesc), C.c_void_p]),
     "g4c_host_guillard": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
     "g4c_debug_profile": (C.c_int, [C.c_int32, C.c_void_p]),

@@ -41,6 +41,7 @@ int interp_launch(const G4cInterpDesc& d, cudaStream_t st);
 int step_update_launch(const G4cStepUpdateDesc& d, cudaStream_t st);
 int halo_launch(const G4cHaloDesc& d, cudaStream_t st, bool pack);
 int knn_launch(const G4cKnnDesc& d, cudaStream_t st);
+int halo_put_launch(const G4cHaloPutDesc& d, cudaStream_t st);
 int tc2_test_launch(int test, const float* A, const void* Wpack, float inv_scale, const float* P, float* D, int flags, cudaStream_t st);
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -205,6 +206,22 @@ int g4c_halo_pack(const G4cHaloDesc* d, void* stream) {
 int g4c_halo_unpack(const G4cHaloDesc* d, void* stream) {
     if (!d || !d->idx || !d->src || !d->dst || (d->width & 3)) { set_error("g4c_halo_unpack: bad descriptor"); return G4C_EINVAL; }
     return halo_launch(*d, static_cast<cudaStream_t>(stream), false);
+}
+
+int g4c_halo_put(const G4cHaloPutDesc* d, void* stream) {
+    if (!d || !d->state || d->n_rows < 0 || d->n_peers < 0 || d->n_peers > G4C_MAX_PEERS || (d->width & 3) || d->width < 4) {
+        set_error("g4c_halo_put: bad descriptor"); return G4C_EINVAL; }
+    if (d->n_rows > 0 && (!d->src || !d->send_idx)) { set_error("g4c_halo_put: NULL source"); return G4C_EINVAL; }
+    if (d->n_recv < 0 || d->mail_stride < 0 || (d->mail_stride & 3) || (d->n_recv > 0 && (!d->mail || !d->ghost || !aligned16(d->mail) || !aligned16(d->ghost)))) {
+        set_error("g4c_halo_put: bad mailbox"); return G4C_EINVAL; }
+    if (d->n_recv * d->width > d->mail_stride) { set_error("g4c_halo_put: n_recv rows do not fit a mailbox half"); return G4C_EINVAL; }
+    if (d->seg_start[0] != 0 || d->seg_start[d->n_peers] != d->n_rows) { set_error("g4c_halo_put: seg_start does not cover n_rows"); return G4C_EINVAL; }
+    for (int p = 0; p < d->n_peers; ++p) {
+        if (!d->peer_flag[p] || !d->my_flag[p]) { set_error("g4c_halo_put: NULL flag for neighbour %d", p); return G4C_EINVAL; }
+        if (d->seg_start[p + 1] < d->seg_start[p] || (d->seg_start[p + 1] > d->seg_start[p] && !d->dst[p])) {
+            set_error("g4c_halo_put: bad segment for neighbour %d", p); return G4C_EINVAL; }
+    }
+    return halo_put_launch(*d, static_cast<cudaStream_t>(stream));
 }
 
 int g4c_plan_knn(const G4cKnnDesc* d, void* stream) {

@@ -1,6 +1,7 @@
 // misc.cu — bandwidth-bound helpers of the hot path: segmented reduce (pooling), REMuS geometry
 // (projection, edge->node least squares, kNN interpolation), rollout state update, halo staging.
 // All are single-pass, float4-vectorised where the row width allows, one warp (or sub-warp) per row.
+#include <algorithm>
 #include "common.cuh"
 
 namespace g4c {
@@ -133,6 +134,76 @@ __global__ void halo_unpack_kernel(const G4cHaloDesc d) {
         *reinterpret_cast<float4*>(d.dst + (size_t)d.idx[i] * d.width + c4 * 4) =
             *reinterpret_cast<const float4*>(d.src + (size_t)i * d.width + c4 * 4);
     }
+}
+
+// ---- halo exchange over peer memory: pack + put + signal + wait + unpack in one kernel (see G4cHaloPutDesc)
+__device__ __forceinline__ void st_release_sys(uint64_t* p, uint64_t v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__global__ void __launch_bounds__(256) halo_put_kernel(const G4cHaloPutDesc d) {
+    __shared__ int s_last;
+    // state[0] = exchanges completed so far on this rank (the same number on every rank: the exchange sequence is collective);
+    // it is rewritten only after EVERY block has passed the second counter below, so every block reads the same value here
+    const uint64_t seq = *reinterpret_cast<volatile uint64_t*>(d.state);
+    const uint64_t epoch = seq + 1;
+    const size_t half = (seq & 1) ? (size_t)d.mail_stride : 0;       // the mailbox half this exchange uses (see g4c.h)
+    const int V = d.width / 4;
+    const int64_t total = d.n_rows * V;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += stride) {
+        const int64_t i = t / V;
+        const int c4 = (int)(t % V);
+        int p = 0;
+        while (p + 1 < d.n_peers && i >= d.seg_start[p + 1]) ++p;
+        const float4 v = *reinterpret_cast<const float4*>(d.src + (size_t)d.send_idx[i] * d.width + c4 * 4);
+        *reinterpret_cast<float4*>(d.dst[p] + half + (size_t)(i - d.seg_start[p]) * d.width + c4 * 4) = v;       // NVLink store
+    }
+    __threadfence_system();                       // this thread's peer stores are performed system-wide
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(reinterpret_cast<unsigned long long*>(d.state + 1), 1ull) == (unsigned long long)gridDim.x - 1);
+    __syncthreads();
+    if (s_last) {
+        // the last block to finish its stores: every block's stores are fenced -> tell the neighbours
+        __threadfence_system();
+        if ((int)threadIdx.x < d.n_peers) st_release_sys(d.peer_flag[threadIdx.x], epoch);
+    }
+    // every block waits for the neighbours' rows (the flags are in THIS rank's memory: the polling stays on this GPU)
+    if ((int)threadIdx.x < d.n_peers) {
+        const long long t0 = clock64();
+        while (ld_acquire_sys(d.my_flag[threadIdx.x]) < epoch) {
+            if (clock64() - t0 > 8000000000ll) __trap();         // ~4 s at 2 GHz: a protocol error must not hang the GPU
+        }
+    }
+    __syncthreads();
+    // mailbox half -> the ghost rows of the feature array (L2 loads: the rows were written by other GPUs)
+    const int64_t total_in = d.n_recv * V;
+    const float4* mail = reinterpret_cast<const float4*>(d.mail + half);
+    float4* ghost = reinterpret_cast<float4*>(d.ghost);
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total_in; t += stride) ghost[t] = __ldcg(mail + t);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(reinterpret_cast<unsigned long long*>(d.state + 2), 1ull) == (unsigned long long)gridDim.x - 1) {
+            d.state[1] = 0;
+            d.state[2] = 0;
+            __threadfence();
+            *reinterpret_cast<volatile uint64_t*>(d.state) = epoch;
+        }
+    }
+}
+
+int halo_put_launch(const G4cHaloPutDesc& d, cudaStream_t st) {
+    const int64_t work = std::max(d.n_rows, d.n_recv) * (d.width / 4);
+    // every block spins until the neighbours answer, so the grid must be co-resident: at most one block per SM
+    const int grid = (int)std::min<int64_t>(std::max<int64_t>(grid_for(work, 256), 1), device_sms());
+    halo_put_kernel<<<grid, 256, 0, st>>>(d);
+    count_launch();
+    return check_launch("halo_put_kernel");
 }
 
 int seg_reduce_launch(const G4cSegReduceDesc& d, cudaStream_t st) {

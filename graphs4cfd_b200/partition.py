@@ -106,6 +106,7 @@ class Xchg:
         self.recv_off = int(recv_off)
         self.n_send, self.n_recv = int(sum(self.send_splits)), int(sum(self.recv_splits))
         self.active = True      # set False when no rank sends anything (then every rank skips the collective)
+        self.mail_base = None   # per destination rank: the row of ITS receive order where this rank's rows land (peer-memory exchange)
 
 
 def _by_owner(ids: np.ndarray, owner: np.ndarray):
@@ -253,16 +254,27 @@ def build_rank_plans(g, params, world: int):
             P["n_edge_recv"] = recv_edges.size
             P["e_hl"] = lv["e_hl"][torch.from_numpy(own)]
     # exchanges in which nobody sends anything are skipped by every rank
+    talk = [set() for _ in range(world)]      # ranks that exchange rows with rank r in ANY exchange (symmetric by construction)
+    mail_rows = 0                             # most rows any rank receives in one exchange (size of a mailbox half, PeerHalo)
     for l in range(nl):
         for key in ("mp_xchg", "up_xchg", "child_xchg", "edge_xchg"):
             xs = [plans[r]["levels"][l].get(key) for r in range(world)]
             if xs[0] is None:
                 continue
             active = any(x.n_send > 0 for x in xs)
-            for x in xs:
+            for r, x in enumerate(xs):
                 x.active = active
+                # rows of rank r land in rank q's receive order behind the rows of the ranks before r (grouped by source)
+                x.mail_base = [sum(xs[q].recv_splits[:r]) for q in range(world)]
+                mail_rows = max(mail_rows, x.n_recv if active else 0)
+                for q in range(world):
+                    if x.send_splits[q] or x.recv_splits[q]:
+                        talk[r].add(q)
+                        talk[q].add(r)
     for r in range(world):
         plans[r]["eperm0"] = levels[0]["eperm"]
+        plans[r]["neighbours"] = sorted(talk[r])
+        plans[r]["mail_rows"] = int(mail_rows)
     return plans, prog
 
 
@@ -436,6 +448,13 @@ class _CudaBackend:
         import torch.distributed as dist
         eng = self.eng
         send_idx = torch.from_numpy(x.send_idx).to(eng.device, torch.int32)
+        if eng.p2p is not None:
+            put = eng.p2p.exchange(buf, x, send_idx)
+            self._flush()
+            self.steps.append(put)
+            self.labels.append(f"halo put (peer memory) send={x.n_send} recv={x.n_recv} rows")
+            eng.exchanges_per_step += 1
+            return
         stage = torch.empty(max(x.n_send, 1), eng.H, device=eng.device, dtype=torch.float32)
         eng.buffer_bytes += stage.numel() * 4
 
@@ -450,16 +469,92 @@ class _CudaBackend:
         eng.exchanges_per_step += 1
 
 
+def peer_memory_available(world: int) -> bool:
+    """True when the process group is NCCL over GPUs of ONE node (every rank can map every other rank's memory) and torch
+    has the symmetric-memory allocator.  Decided from facts every rank sees alike, so all ranks take the same transport."""
+    import os
+    import torch.distributed as dist
+    if world < 2 or not dist.is_available() or not dist.is_initialized() or dist.get_backend() != "nccl":
+        return False
+    if int(os.environ.get("LOCAL_WORLD_SIZE", world)) != world or world > torch.cuda.device_count():
+        return False
+    try:
+        import torch.distributed._symmetric_memory as symm_mem  # noqa: F401
+    except ImportError:
+        return False
+    return True
+
+
+class PeerHalo:
+    """Halo exchange over NVLink peer memory.  Every rank owns a mailbox (two halves of ``mail_rows`` feature rows) and a flag
+    array in symmetric memory (torch.distributed._symmetric_memory: every rank maps every other rank's allocation); one
+    kernel per exchange (g4c_halo_put, include/g4c.h) packs the rows, stores them straight into the neighbours' mailboxes,
+    publishes the exchange number to their flags, waits for theirs and copies the received rows behind the own rows of the
+    feature array.  No NCCL call and no separate pack or unpack launch; the feature arrays themselves stay ordinary memory."""
+
+    def __init__(self, eng, group, mail_rows, neighbours, width):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        self.eng, self.rank, self.world, self.width = eng, eng.rank, eng.world, int(width)
+        self.peers = list(neighbours)
+        if len(self.peers) > _lib.MAX_PEERS:
+            raise RuntimeError(f"peer-memory halo: {len(self.peers)} neighbours (max {_lib.MAX_PEERS})")
+        self.mail_stride = max(int(mail_rows), 1) * self.width
+        self.mail = symm_mem.empty(2 * self.mail_stride, dtype=torch.float32, device=eng.device)
+        self.flags = symm_mem.empty(self.world, dtype=torch.int64, device=eng.device)
+        self.mail.zero_()
+        self.flags.zero_()
+        torch.cuda.synchronize(eng.device)
+        self._handles = (symm_mem.rendezvous(self.mail, group), symm_mem.rendezvous(self.flags, group))
+        self.mail_ptrs = list(self._handles[0].buffer_ptrs)
+        self.flag_ptrs = list(self._handles[1].buffer_ptrs)
+        self.state = torch.zeros(4, dtype=torch.int64, device=eng.device)
+        eng.buffer_bytes += self.mail.numel() * 4
+        dist.barrier(group)          # nobody stores into a mailbox or a flag that is not zeroed and mapped yet
+
+    def exchange(self, buf, x, send_idx):
+        """The g4c_halo_put launch of exchange ``x`` on the feature array ``buf`` (returns the callable)."""
+        from . import _lib
+        width = int(buf.shape[1])
+        if width != self.width or x.n_recv * width > self.mail_stride:
+            raise RuntimeError("peer-memory halo: the exchange does not fit the mailbox")
+        d = _lib.HaloPutDesc()
+        d.n_rows, d.width, d.n_peers = int(x.n_send), width, len(self.peers)
+        d.src, d.send_idx = buf.data_ptr(), send_idx.data_ptr()
+        d.state = self.state.data_ptr()
+        d.mail_stride, d.mail = self.mail_stride, self.mail.data_ptr()
+        d.ghost, d.n_recv = buf.data_ptr() + x.recv_off * width * 4, int(x.n_recv)
+        off = 0
+        for i, q in enumerate(self.peers):
+            d.seg_start[i] = off
+            n = x.send_splits[q]
+            d.dst[i] = (self.mail_ptrs[q] + x.mail_base[q] * width * 4) if n else None
+            d.peer_flag[i] = self.flag_ptrs[q] + self.rank * 8
+            d.my_flag[i] = self.flag_ptrs[self.rank] + q * 8
+            off += n
+        d.seg_start[len(self.peers)] = off
+        if off != x.n_send or any(x.recv_splits[q] for q in range(self.world) if q not in self.peers):
+            raise RuntimeError("peer-memory halo: rows travel between ranks outside the neighbour set")
+        keep = (d, buf, send_idx)
+
+        def run():
+            _lib.launch("g4c_halo_put", keep[0], buf, send_idx, self.state, self.mail)
+
+        return run
+
+
 class PartitionedRollout:
     """Rank-local slice of a MuS-GNN rollout.  API mirrors Rollout (solve / step_only / pred / node_in)."""
 
     def __init__(self, params, graph, rank: int, world: int, precision="auto", device="cuda", cuda_graph=False, renumber=True,
-                 overlap=False):
+                 overlap=False, halo="auto"):
         """overlap: the halo exchange of a tensor-core message-passing block runs on NCCL's stream behind the block's first
         kernel (the per-node products of the own rows) instead of in front of the block.  Off by default: measured on B200
         (profiles/r2i_*, r2j_*) the extra launch for the ghost rows' products costs more than the hidden latency saves."""
         from . import ops
         self.overlap = overlap
+        self.p2p = None
         self.device = LIB.cuda_device(device)
         self.rank, self.world, self.precision = rank, world, precision
         node_perm = None
@@ -506,6 +601,19 @@ class PartitionedRollout:
         ops.rowmlp(self.pack("edge_encoder"), [(edge_attr.to(dev), None, 1.0)], act="selu", out=self.e0, precision=row_prec)
         self.e0._g4c_key = ("e0",)
         self.pred = torch.empty(max(self.N, 1), self.nf, device=dev, dtype=torch.float32)
+        # halo transport: "nccl" = pack kernel + all_to_all_single; "p2p" = one kernel over NVLink peer memory (PeerHalo);
+        # "auto" = p2p when every rank of the job is a GPU of this node (measured on 8 B200: 181.3 against 176.3 steps/s,
+        # profiles/r2r_*), else nccl
+        if halo == "auto":
+            halo = "p2p" if peer_memory_available(world) and not overlap else "nccl"
+        self.halo = halo if world > 1 else "nccl"
+        if self.halo == "p2p":
+            if overlap:
+                raise ValueError("overlap=True moves the exchange to NCCL's stream: it needs halo='nccl'")
+            import torch.distributed as dist
+            self.p2p = PeerHalo(self, dist.group.WORLD, plan["mail_rows"], plan["neighbours"], self.H)
+        elif self.halo != "nccl":
+            raise ValueError(f"halo={halo!r} (nccl, p2p)")
         be = _CudaBackend(self)
         be.node_in, be.e0, be.e_hl, be.children, be.pool, be.parent_local, be.pred = \
             self.node_in, self.e0, self.e_hl, self.children, self.pool, self.parent_local, self.pred
@@ -571,6 +679,6 @@ def partitioned_rollout(params, graph, rank: int, world: int, **kw):
     nn/remus_gnn.py:19-57) get the edge-halo partition of partition_remus.py, everything else the node-halo one."""
     if any(k.startswith("angle_encoder") for k in params):
         from .partition_remus import PartitionedRemusRollout
-        kw = {k: v for k, v in kw.items() if k not in ("overlap", "renumber")}      # MuS-engine options
+        kw = {k: v for k, v in kw.items() if k not in ("overlap", "renumber", "halo")}      # MuS-engine options
         return PartitionedRemusRollout(params, graph, rank, world, **kw)
     return PartitionedRollout(params, graph, rank, world, **kw)

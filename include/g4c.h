@@ -265,6 +265,39 @@ typedef struct {
     int32_t dual, _pad2;
 } G4cRowTcDesc;
 
+/* Halo exchange as ONE kernel over NVLink peer memory (no reference counterpart; replaces pack kernel + NCCL all_to_all_single
+ * + received-rows placement of the node-range partition).  Every rank owns a MAILBOX in symmetric memory (every rank maps every
+ * other rank's): two halves of mail_stride floats.  One call = one exchange of the collective sequence:
+ *   1. rows send_idx[seg_start[d] .. seg_start[d+1]) of `src` are stored straight into neighbour d's mailbox at dst[d] (peer
+ *      pointer, already offset to where this rank's rows land in d's receive order) + the half of this exchange;
+ *   2. the stores are fenced system-wide and the exchange number is published to every neighbour's flag slot (st.release.sys);
+ *   3. the kernel waits until every neighbour's number has arrived in this rank's slots (ld.acquire.sys, local polling);
+ *   4. the n_recv rows of this rank's mailbox half are copied to `ghost` (the ghost rows of the local feature array).
+ * Halves alternate with the exchange number: a neighbour can run at most one exchange ahead (it needs this rank's flag to get
+ * past step 3), so it never overwrites rows this rank has not copied out yet.  All ranks must issue the same sequence of calls;
+ * neighbour sets must be symmetric and every neighbour is signalled even when no rows go to it.
+ * `state` is rank-local device memory shared by ALL exchanges of one engine, zero at plan time: state[0] = exchanges completed,
+ * state[1], state[2] = block counters.  A neighbour that does not answer within ~4 s traps the kernel instead of hanging the
+ * GPU.  CUDA-graph capturable.  The grid is at most one block per SM (all blocks wait in step 3, so they must be co-resident). */
+#define G4C_MAX_PEERS 8
+typedef struct {
+    int64_t n_rows;                   /* rows sent to all neighbours together                 */
+    int32_t width;                    /* floats per row, multiple of 4                        */
+    int32_t n_peers;                  /* neighbours (sent to AND waited for), <= G4C_MAX_PEERS */
+    const float* src;                 /* local feature array                                  */
+    const int32_t* send_idx;          /* [n_rows] local rows, grouped by neighbour            */
+    int32_t seg_start[G4C_MAX_PEERS + 1];
+    int32_t _pad;
+    float* dst[G4C_MAX_PEERS];        /* peer pointers into the neighbours' mailboxes, half 0 (NULL when nothing is sent to d) */
+    uint64_t* peer_flag[G4C_MAX_PEERS];   /* this rank's slot in neighbour d's flag array     */
+    const uint64_t* my_flag[G4C_MAX_PEERS];   /* neighbour d's slot in this rank's flag array */
+    uint64_t* state;                  /* [3] rank-local                                       */
+    int64_t mail_stride;              /* floats between the two halves of a mailbox (same on every rank) */
+    const float* mail;                /* this rank's mailbox, half 0                          */
+    float* ghost;                     /* [n_recv, width] where the received rows go           */
+    int64_t n_recv;                   /* rows received from all neighbours together           */
+} G4cHaloPutDesc;
+
 /* Plan-time graph building on the device: exact 2-D k-nearest neighbours on a uniform cell grid.
  * Replaces: torch_cluster.knn_graph behind connect_knn (transforms/connect.py:58: k in-edges per node, neighbour -> centre,
  * ascending distance) and torch_cluster.knn behind get_knn_interpolate_weights (transforms/interpolate.py:125).
@@ -298,6 +331,7 @@ G4C_API int g4c_interp_fwd(const G4cInterpDesc* d, void* stream);
 G4C_API int g4c_step_update(const G4cStepUpdateDesc* d, void* stream);
 G4C_API int g4c_halo_pack(const G4cHaloDesc* d, void* stream);
 G4C_API int g4c_halo_unpack(const G4cHaloDesc* d, void* stream);
+G4C_API int g4c_halo_put(const G4cHaloPutDesc* d, void* stream);
 G4C_API int g4c_plan_knn(const G4cKnnDesc* d, void* stream);
 
 /* number of kernels this library has launched since load (bench.py reports it as gpu_launches) */

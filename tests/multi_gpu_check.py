@@ -36,7 +36,7 @@ def main():
         g = M.build_mus_mesh(n, 6, M.auto_cells(n, 3), seed=5)
         params = init_params(mus_arch(H, 3), seed=2)
         eng = PartitionedRollout(params, g, rank, world, precision=precision, device=dev,
-                                 cuda_graph=os.environ.get("G4C_GRAPH", "0") == "1")
+                                 cuda_graph=os.environ.get("G4C_GRAPH", "0") == "1", halo=os.environ.get("G4C_HALO", "auto"))
     out = eng.gather(eng.solve(steps), n).cpu()
     ok = True
     if rank == 0:
@@ -44,8 +44,8 @@ def main():
         rel = float((out - want).norm() / want.norm())
         single = Rollout(params, g, precision=precision, device=dev).solve(steps).cpu()
         rel1 = float((out - single).norm() / single.norm())
-        print(f"world={world} precision={precision}: rel-L2 vs oracle {rel:.3e}, vs single-GPU engine {rel1:.3e}, "
-              f"exchanges/step={eng.exchanges_per_step}")
+        print(f"world={world} precision={precision} halo={getattr(eng, 'halo', 'nccl')} graph={os.environ.get('G4C_GRAPH', '0')}: "
+              f"rel-L2 vs oracle {rel:.3e}, vs single-GPU engine {rel1:.3e}, exchanges/step={eng.exchanges_per_step}")
         ok = rel <= (5e-5 if precision == "fp32" else 2e-4) and rel1 <= (5e-6 if precision == "fp32" else 2e-4)
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, 0)

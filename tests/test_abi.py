@@ -41,7 +41,7 @@ def test_ctypes_struct_sizes_match_header(built_lib, tmp_path):
              "G4cProjectDesc": built_lib.ProjectDesc, "G4cEdgeToNodeDesc": built_lib.EdgeToNodeDesc,
              "G4cInterpDesc": built_lib.InterpDesc, "G4cStepUpdateDesc": built_lib.StepUpdateDesc,
              "G4cHaloDesc": built_lib.HaloDesc, "G4cEdgeDesc": built_lib.EdgeDesc, "G4cRowTcDesc": built_lib.RowTcDesc,
-             "G4cKnnDesc": built_lib.KnnDesc}
+             "G4cKnnDesc": built_lib.KnnDesc, "G4cHaloPutDesc": built_lib.HaloPutDesc}
     src = tmp_path / "sz.c"
     body = "".join(f'printf("{n} %zu\\n", sizeof({n}));' for n in pairs)
     src.write_text(f'#include <stdio.h>\n#include "g4c.h"\nint main(void){{{body}return 0;}}\n')
@@ -59,7 +59,7 @@ def test_ctypes_field_offsets_match_header(built_lib, tmp_path):
              "G4cMpDesc": built_lib.MpDesc, "G4cEdgeDesc": built_lib.EdgeDesc, "G4cRowTcDesc": built_lib.RowTcDesc,
              "G4cSegReduceDesc": built_lib.SegReduceDesc, "G4cProjectDesc": built_lib.ProjectDesc,
              "G4cEdgeToNodeDesc": built_lib.EdgeToNodeDesc, "G4cInterpDesc": built_lib.InterpDesc,
-             "G4cStepUpdateDesc": built_lib.StepUpdateDesc, "G4cHaloDesc": built_lib.HaloDesc, "G4cKnnDesc": built_lib.KnnDesc}
+             "G4cStepUpdateDesc": built_lib.StepUpdateDesc, "G4cHaloDesc": built_lib.HaloDesc, "G4cKnnDesc": built_lib.KnnDesc, "G4cHaloPutDesc": built_lib.HaloPutDesc}
     lines = []
     for cname, cls in pairs.items():
         for fname, *_ in cls._fields_:

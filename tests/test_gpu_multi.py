@@ -11,13 +11,16 @@ from conftest import ROOT
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("halo,graph", [("nccl", "0"), ("p2p", "0"), ("p2p", "1")])
 @pytest.mark.parametrize("precision", ["fp32", "fp16x3"])
-def test_partitioned_rollout_matches_single_gpu(precision):
+def test_partitioned_rollout_matches_single_gpu(precision, halo, graph):
+    """halo = nccl: pack kernel + all_to_all_single; p2p: one kernel over NVLink peer memory (g4c_halo_put), eager and
+    captured in the step's CUDA graph."""
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
     world = 2 if n < 4 else 4
-    env = dict(os.environ, G4C_PRECISION=precision)
+    env = dict(os.environ, G4C_PRECISION=precision, G4C_HALO=halo, G4C_GRAPH=graph)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", "29611", os.path.join(ROOT, "tests", "multi_gpu_check.py")]
     res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)

@@ -3,7 +3,7 @@ of PartitionedRollout bracketed by CUDA events, averaged over `--reps` steps aft
 exchange (pack kernel + NCCL all_to_all_single) and how much is kernels, per level.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29655 \
-        tools/partition_timeline.py [--nodes 1000000] [--reps 5]
+        tools/partition_timeline.py [--nodes 1000000] [--reps 5] [--halo nccl|p2p]
 """
 import argparse
 import collections
@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--nodes", type=int, default=1_000_000)
     ap.add_argument("--hidden", type=int, default=128)
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--halo", default="nccl", choices=["nccl", "p2p"])
     a = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -29,7 +30,7 @@ def main():
     from graphs4cfd_b200.archs import init_params, mus_arch
     from graphs4cfd_b200.partition import PartitionedRollout
     g = M.build_mus_mesh(a.nodes, 6, M.auto_cells(a.nodes, 3), seed=0)
-    eng = PartitionedRollout(init_params(mus_arch(a.hidden, 3), seed=0), g, rank, world, device=dev, cuda_graph=False)
+    eng = PartitionedRollout(init_params(mus_arch(a.hidden, 3), seed=0), g, rank, world, device=dev, cuda_graph=False, halo=a.halo)
     for _ in range(3):
         eng.step_only()
     torch.cuda.synchronize(dev)
@@ -50,7 +51,7 @@ def main():
         total += ev[0].elapsed_time(ev[n])
     if rank == 0:
         by_kind = collections.defaultdict(float)
-        print(f"# partitioned MuS-3 step, {a.nodes} nodes, hidden {a.hidden}, world {world}, rank 0, eager (events between step functions), "
+        print(f"# partitioned MuS-3 step, {a.nodes} nodes, hidden {a.hidden}, world {world}, halo {a.halo}, rank 0, eager (events between step functions), "
               f"{a.reps} steps averaged; step total {total / a.reps:.3f} ms")
         for lab, t in zip(eng.step_labels, acc):
             t /= a.reps
