@@ -1,5 +1,5 @@
 """Architecture dictionaries of the reference models (same keys and tuple forms as the ``arch`` dicts in
-nn/mus_gnn.py:226-258 and nn/remus_gnn.py:16-58) and seeded default-init parameters for them.
+nn/mus_gnn.py:226-258, nn/remus_gnn.py:16-58 and nn/mugs_gnn.py:16-41) and seeded default-init parameters for them.
 Used by the benchmark and the tests (no checkpoints can be downloaded; the shipped ones stay in the reference)."""
 from collections import OrderedDict
 
@@ -45,6 +45,29 @@ def mus_arch(H: int = 128, levels: int = 3, node_in: int = 5, nf: int = 3, adv: 
         a["up_mp21"] = up()
         for i in range(1, n1 + 1):
             a[f"mp12{i}"] = mp()
+    a["decoder"] = (H, (H, H, nf), False)
+    return a
+
+
+def mugs_arch(H: int = 128, levels: int = 2, node_in: int = 5, nf: int = 3):
+    """MuGS-GNN (nn/mugs_gnn.py:16-41, 140-171, 302-340): the first block behind every up-sampling takes 2H-wide node features."""
+    mp = lambda: ((3 * H, (H, H, H), True), (2 * H, (H, H, H), True))
+    wide = lambda: ((5 * H, (H, H, H), True), (3 * H, (H, H, H), True))
+    a = OrderedDict()
+    for l in range(1, levels + 1):
+        a["edge_encoder" + ("" if l == 1 else str(l))] = (2, (H, H, H), False)
+    a["node_encoder"] = (node_in, (H, H, H), False)
+    for i in range(1, 5):
+        a[f"mp11{i}"] = mp()
+    for l in range(2, levels):
+        a[f"mp{l}11"], a[f"mp{l}12"] = mp(), mp()
+    for i in range(1, 5):
+        a[f"mp{levels}{i}"] = mp()
+    for l in range(levels - 1, 1, -1):
+        a[f"mp{l}21"], a[f"mp{l}22"] = wide(), mp()
+    a["mp121"] = wide()
+    for i in range(2, 5):
+        a[f"mp12{i}"] = mp()
     a["decoder"] = (H, (H, H, nf), False)
     return a
 

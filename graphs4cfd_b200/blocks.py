@@ -74,7 +74,7 @@ class _Cache:
         hit = self._d.get(flat)
         if hit is not None and all(r() is not None for r in hit[0]):
             return hit[1]
-        if len(self._d) > 16:
+        if len(self._d) > 64:
             self._d.clear()
         value = build()
         self._d[flat] = (tuple(weakref.ref(t) for t in tensors), value)
@@ -321,6 +321,28 @@ def interp_layout(y_idx: torch.Tensor):
     return n_y, k
 
 
+def knn_interpolate(x: torch.Tensor, y_idx: torch.Tensor, x_idx: torch.Tensor, weights: torch.Tensor):
+    """Mirror of blocks.py:34-48 (the up-sampling of the MuGS models, nn/mugs_gnn.py:120): y[i] = sum_m w[i, m] x[x_idx[i, m]] /
+    sum_m w[i, m] over the k candidates of every target, one g4c_interp_fwd launch."""
+    require_cuda_f32(x, weights)
+    _no_grad_guard(x)
+    n_y, k = _TOPO_CACHE.get(("interp",) + _Cache.key(y_idx), lambda: interp_layout(y_idx))
+    y = torch.empty(n_y, x.size(1), device=x.device, dtype=torch.float32)
+    return ops.interp(x, _i32(x_idx), weights.reshape(-1), k, n_y, y, None)
+
+
+def restriction(graph, coarse_mask, edge_attr, edge_index, num_nodes, device) -> None:
+    """Mirror of blocks.py:9-32 (MuGS down-sampling: keep the nodes of ``coarse_mask``, renumber the coarse level's edges).
+    The renumbered edge list depends on the mesh only, so it is built once per (mask, edge list) and reused by every time step;
+    handing back the SAME tensor also lets the block that follows find its cached topology."""
+    def build():
+        mask2idx = -torch.ones(num_nodes, dtype=torch.long, device=edge_index.device)
+        mask2idx[coarse_mask] = torch.arange(int(coarse_mask.sum()), dtype=torch.long, device=edge_index.device)
+        return mask2idx[edge_index]
+    graph.edge_index = _TOPO_CACHE.get(("restrict", int(num_nodes)) + _Cache.key(coarse_mask, edge_index), build)
+    graph.edge_attr = edge_attr
+
+
 class UpEdgeMP(nn.Module):
     """Mirror of blocks.py:384-456."""
 
@@ -379,6 +401,23 @@ def _convert(mod: nn.Module, precision: str):
     return new
 
 
+def _wrap_helper(mod, fname, ours, first_tensor):
+    """Rebind the module-level helper ``fname`` of a reference model module to a dispatcher: CUDA tensors take our function,
+    anything else the reference's own."""
+    orig = getattr(mod, fname, None) if mod is not None else None
+    if orig is None or orig is ours or getattr(orig, "_g4c_wrapper", False):
+        return
+
+    def dispatch(*args, **kwargs):
+        if first_tensor(args, kwargs).is_cuda:
+            return ours(*args, **kwargs)
+        return orig(*args, **kwargs)
+    dispatch._g4c_wrapper = True
+    dispatch.__wrapped__ = orig
+    dispatch.__name__ = fname
+    setattr(mod, fname, dispatch)
+
+
 def accelerate(model: nn.Module, precision: str = "auto") -> nn.Module:
     """Replace every graphs4cfd block of ``model`` by its libg4c counterpart, in place, keeping the
     Parameters and state-dict keys.  ``model.forward``/``solve`` then run unchanged reference code
@@ -392,15 +431,10 @@ def accelerate(model: nn.Module, precision: str = "auto") -> nn.Module:
     # by every model of that module, so it is wrapped rather than replaced: CUDA tensors take g4c_edge_to_node_fwd, anything
     # else (another, un-accelerated model living on the CPU) still reaches the reference's own function.
     mod = sys.modules.get(type(model).__module__)
-    orig = getattr(mod, "edgeScalarToNodeVector", None) if mod is not None else None
-    if orig is not None and orig is not edgeScalarToNodeVector and not getattr(orig, "_g4c_wrapper", False):
-        def dispatch(edge_attr, *args, **kwargs):
-            if edge_attr.is_cuda:
-                return edgeScalarToNodeVector(edge_attr, *args, **kwargs)
-            return orig(edge_attr, *args, **kwargs)
-        dispatch._g4c_wrapper = True
-        dispatch.__wrapped__ = orig
-        mod.edgeScalarToNodeVector = dispatch
+    # (the MuGS forwards call knn_interpolate and restriction the same way, nn/mugs_gnn.py:107, 120)
+    for fname, first_tensor in (("edgeScalarToNodeVector", lambda a, k: a[0]), ("knn_interpolate", lambda a, k: a[0]),
+                                ("restriction", lambda a, k: a[2] if len(a) > 2 else k["edge_attr"])):
+        _wrap_helper(mod, fname, globals()[fname], first_tensor)
     return model
 
 
@@ -411,6 +445,7 @@ def patch_reference(gfd) -> None:
         m = getattr(gfd.nn, sub, None)
         if m is None:
             continue
-        for name in ("MLP", "MP", "DownMP", "UpMP", "EdgeMP", "DownEdgeMP", "UpEdgeMP", "edgeScalarToNodeVector"):
+        for name in ("MLP", "MP", "DownMP", "UpMP", "EdgeMP", "DownEdgeMP", "UpEdgeMP", "edgeScalarToNodeVector",
+                     "knn_interpolate", "restriction"):
             if hasattr(m, name):
                 setattr(m, name, globals()[name])

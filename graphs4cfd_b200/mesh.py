@@ -307,6 +307,42 @@ def build_mus_mesh(n: int, k: int = 6, cells: Sequence[float] = (), seed: int = 
     return m
 
 
+def build_mugs_mesh(n: int, k: int = 6, levels: int = 2, seed: int = 0, points: str = "jittered", interp_k: int = None,
+                    edge_scale=None, device=None) -> Mesh:
+    """MuGS-GNN input with ``levels`` (2..4) node-nested levels in the layouts of GuillardCoarseningAndConnectKNN
+    (transforms/mugs.py:58-88: level-l edges in LEVEL-1 node ids, coarse masks over the level-1 nodes) and BuildKnnInterpWeights
+    (transforms/interpolate.py:147-155).  ``edge_scale``: per-level characteristic edge length (default: the level's mean)."""
+    assert 2 <= levels <= 4
+    interp_k = k if interp_k is None else interp_k
+    edge_scale = (None,) * levels if edge_scale is None else edge_scale
+    pos = jittered_points(n, seed) if points == "jittered" else uniform_points(n, seed)
+    if device is not None:
+        pos = pos.to(device)
+    m = Mesh(pos=pos, field=_fields(pos, 3), glob=torch.full((n, 1), 0.3, device=pos.device), omega=_omega(pos))
+
+    def scaled(ei, ea, s):
+        r = float(ea.norm(dim=1).mean()) if s is None else s
+        return ei, ea / (2 * r)
+
+    m.edge_index, m.edge_attr = scaled(*knn_edges(pos, k), edge_scale[0])
+    ei_l, mask_prev, idx_prev = m.edge_index, None, torch.arange(n, device=pos.device)
+    for l in range(2, levels + 1):
+        keep = guillard_coarsening(ei_l, idx_prev.numel())              # over the nodes of level l-1
+        mask = torch.zeros(n, dtype=torch.bool, device=pos.device)
+        mask[idx_prev[keep]] = True
+        idx = mask.nonzero().squeeze(1)                                 # level-1 ids of the level-l nodes
+        ei_l, ea = scaled(*knn_edges(pos[idx], k), edge_scale[l - 1])
+        setattr(m, f"coarse_mask{l}", mask)
+        setattr(m, f"edge_index{l}", idx[ei_l])
+        setattr(m, f"edge_attr{l}", ea)
+        y, x, w = knn_interp_weights(pos[idx], pos[idx_prev], interp_k)
+        setattr(m, f"y_idx_{l}{l - 1}", y)
+        setattr(m, f"x_idx_{l}{l - 1}", x)
+        setattr(m, f"weights_{l}{l - 1}", w)
+        idx_prev = idx
+    return m
+
+
 def auto_cells(n: int, levels: int, box=(4.0, 1.0), ratios=(5.0, 20.0, 80.0)):
     """cell sizes giving N_2 ~ N/5, N_3 ~ N/20, N_4 ~ N/80 (the reference example's ratios)."""
     area = box[0] * box[1]

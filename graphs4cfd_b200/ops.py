@@ -81,7 +81,7 @@ class MlpPack:
                 raise RuntimeError("graphs4cfd_b200: all hidden widths of an MLP must be equal")
         self._linears = [(W.detach().float(), b.detach().float()) for W, b in linears]
         self._ln_raw = None if ln is None else (ln[0].detach().float(), ln[1].detach().float())
-        self._tc_row, self._tc_edge = {}, None
+        self._tc_row, self._tc_edge, self._tc_node_wide = {}, None, None
         self.W_t, self.b = [], []
         for i, (W, b) in enumerate(linears):
             W = W.detach().float()
@@ -106,8 +106,33 @@ class MlpPack:
             self._tc_row[key] = RowPairPack(self._linears, list(seg_widths), self._ln_raw)
         return self._tc_row[key]
 
-    def tc_edge_ok(self) -> bool:
-        return self.hidden == 128 and self.in_width == 384 and self.out_width == 128
+    def tc_edge_ok(self, feat_width: int = 128) -> bool:
+        """Edge model over cat(e [128], S[src] [feat_width], T[tgt] [feat_width]); feat_width 256 is the first block behind an
+        up-sampling of the MuGS models (nn/mugs_gnn.py:34: mp121 takes cat(interpolated, skip))."""
+        return (self.hidden == 128 and self.out_width == 128 and feat_width in (128, 256)
+                and self.in_width == 128 + 2 * feat_width)
+
+    def tc_node_ok(self, feat_width: int = 128) -> bool:
+        """Node model over cat(aggregate [128], T [feat_width])."""
+        if feat_width == 128:
+            return self.tc_row_ok([128, 128])
+        return (feat_width == 256 and self.hidden == 128 and self.out_width == 128 and self.in_width == 384
+                and self.n_layers >= 2)
+
+    def tc_node_wide(self):
+        """Node model with 256-wide node features: the row kernel keeps linear_1 resident for at most two 128-wide segments,
+        so linear_1 is applied in two launches that add up exactly like the single product would:
+            Q   = T W1[:, 128:]^T + b1          (bare Linear over the two halves of T)
+            out = MLP'(cat(agg, Q))   with linear_1' = [W1[:, :128] | I], bias 0, the later layers unchanged.
+        Returns (RowPairPack of Q, RowPairPack of MLP')."""
+        if self._tc_node_wide is None:
+            W1, b1 = self._linears[0]
+            W1 = W1.detach().float()
+            eye = torch.eye(128, device=W1.device, dtype=torch.float32)
+            first = (torch.cat([W1[:, :128], eye], dim=1).contiguous(), torch.zeros_like(b1.detach().float()))
+            self._tc_node_wide = (RowPairPack([(W1[:, 128:].contiguous(), b1)], [128, 128]),
+                                  RowPairPack([first] + list(self._linears[1:]), [128, 128], self._ln_raw))
+        return self._tc_node_wide
 
     def tc_edge(self):
         """(EdgePairPack, projection of the source features, projection of the target features)."""
@@ -116,8 +141,9 @@ class MlpPack:
             zero = torch.zeros_like(ep.b1)
             # P_r, P_c leave the row kernel already multiplied by the layer-1 scale s (a power of two: exact), so the
             # edge kernel's loaders only add them (G4cEdgeDesc.p_scale = 1)
-            self._tc_edge = (ep, RowPairPack([(ep.W1s, zero)], [128], out_scale=ep.p_scale),
-                             RowPairPack([(ep.W1t, ep.b1)], [128], out_scale=ep.p_scale))
+            segs = [128] * (ep.feat_width // 128)
+            self._tc_edge = (ep, RowPairPack([(ep.W1s, zero)], segs, out_scale=ep.p_scale),
+                             RowPairPack([(ep.W1t, ep.b1)], segs, out_scale=ep.p_scale))
         return self._tc_edge
 
     @classmethod
@@ -164,7 +190,8 @@ class EdgePairPack:
     def __init__(self, linears: Sequence[Tuple[torch.Tensor, torch.Tensor]], ln=None):
         assert 2 <= len(linears) <= 3
         W1, b1 = linears[0]
-        assert W1.shape == (128, 384), "edge MLP of the tensor-core path: hidden 128, input cat(e, s, t)"
+        assert W1.shape in ((128, 384), (128, 640)), "edge MLP of the tensor-core path: hidden 128, input cat(e, s, t)"
+        self.feat_width = fw = (W1.shape[1] - 128) // 2
         W1 = W1.detach().float()
         s1 = weight_scale(W1)
         self.n_layers = len(linears)
@@ -173,8 +200,8 @@ class EdgePairPack:
         self.W_pair.append(pk)
         self.inv_scale.append(inv * rz_compensation(24))          # K = 128: 8 K-steps x 3 split products
         self.p_scale = s1
-        self.W1s = W1[:, 128:256].contiguous()
-        self.W1t = W1[:, 256:384].contiguous()
+        self.W1s = W1[:, 128:128 + fw].contiguous()
+        self.W1t = W1[:, 128 + fw:].contiguous()
         self.b1 = b1.detach().float().contiguous().clone()
         self.bias = [self.b1]
         for W, b in linears[1:]:
@@ -406,31 +433,60 @@ def mp(edge_pack: MlpPack, node_pack: MlpPack, topo: MpTopo, e_in, src_feat, tgt
     path = per-node products of the split first edge layer (g4c_rowmlp_tc_fwd x2), fused edge MLP + aggregation
     (g4c_edge_aggr_fwd), node model (g4c_rowmlp_tc_fwd).  ``ws`` = optional preallocated (P_r, P_c, agg).
     Returns (t_out, e_out|None)."""
-    L.require_cuda_f32(e_in, src_feat, tgt_feat)
+    # node features: one matrix, or (MuGS, first block behind an up-sampling) a tuple of 128-wide matrices standing for their
+    # concatenation cat(parts, dim=1) -- the kernels read the parts in place, nothing is concatenated
+    def parts(x):
+        if isinstance(x, (tuple, list)):
+            L.require_cuda_f32(*x)
+            return list(x)
+        L.require_cuda_f32(x)
+        return [x] if x.shape[1] <= 128 else [x[:, c:c + 128] for c in range(0, int(x.shape[1]), 128)]
+    L.require_cuda_f32(e_in)
+    same = src_feat is tgt_feat
+    s_parts = parts(src_feat)
+    t_parts = s_parts if same else parts(tgt_feat)
     H = edge_pack.hidden
+    fw = sum(int(p.shape[1]) for p in t_parts)
+    if sum(int(p.shape[1]) for p in s_parts) != fw:
+        raise RuntimeError("mp: source and target features must have the same width")
+    n_src, n_tgt = int(s_parts[0].shape[0]), int(t_parts[0].shape[0])
+    tc_ok = edge_pack.tc_edge_ok(fw) and node_pack.tc_node_ok(fw) and all(int(p.shape[1]) == 128 for p in s_parts + t_parts)
     if precision == "auto":
-        precision = "fp16x3" if (edge_pack.tc_edge_ok() and node_pack.tc_row_ok([128, 128])) else "fp32"
+        precision = "fp16x3" if tc_ok else "fp32"
     if precision == "fp16x3":
-        if not (edge_pack.tc_edge_ok() and node_pack.tc_row_ok([128, 128])):
-            raise RuntimeError(f"mp: precision fp16x3 needs hidden=128 (got {H}); use precision='fp32'")
+        if not tc_ok:
+            raise RuntimeError(f"mp: precision fp16x3 needs hidden=128 and 128- or 256-wide node features (got hidden {H}, "
+                               f"features {fw}); use precision='fp32'")
         ep, proj_s, proj_t = edge_pack.tc_edge()
         dev = e_in.device
         P_r, P_c, agg = ws if ws is not None else (None, None, None)
-        if src_feat is tgt_feat:          # GNBlock / EdgeMP: one pass over the features makes both products
+        segs = lambda ps: [(p, None, 1.0) for p in ps]
+        if same and fw == 128:            # GNBlock / EdgeMP: one pass over the features makes both products
             if P_r is None:
-                P_r = torch.empty(src_feat.shape[0], 128, device=dev, dtype=torch.float32)
+                P_r = torch.empty(n_src, 128, device=dev, dtype=torch.float32)
             if P_c is None:
                 P_c = torch.empty_like(P_r)
-            dual_linear_tc(proj_s, proj_t, src_feat, out_a=P_r, out_b=P_c)
-        else:                             # DownEdgeMP: sources and targets are different levels
-            P_r = rowmlp_tc(proj_s, [(src_feat, None, 1.0)], out=P_r)
-            P_c = rowmlp_tc(proj_t, [(tgt_feat, None, 1.0)], out=P_c)
+            dual_linear_tc(proj_s, proj_t, s_parts[0], out_a=P_r, out_b=P_c)
+        else:                             # DownEdgeMP: sources and targets are different levels; MuGS: 256-wide features
+            P_r = rowmlp_tc(proj_s, segs(s_parts), out=P_r)
+            P_c = rowmlp_tc(proj_t, segs(t_parts), out=P_c)
         if agg is None:
-            agg = torch.empty(tgt_feat.shape[0], 128, device=dev, dtype=torch.float32)
+            agg = torch.empty(n_tgt, 128, device=dev, dtype=torch.float32)
         agg, e_out = edge_aggr(ep, topo, e_in, P_r, P_c, aggr=aggr, act_e=act_e, want_e=want_e, e_out=e_out, agg_out=agg,
                                 p_prescaled=True)
-        t_out = rowmlp_tc(node_pack.tc_row([128, 128]), [(agg, None, 1.0), (tgt_feat, None, 1.0)], act=act_t, out=t_out)
+        if fw == 128:
+            t_out = rowmlp_tc(node_pack.tc_row([128, 128]), [(agg, None, 1.0), (t_parts[0], None, 1.0)], act=act_t, out=t_out)
+        else:
+            # P_r is free again once the edge kernel has run: it holds Q, the target features' share of the node model's linear_1
+            q_pack, wide_pack = node_pack.tc_node_wide()
+            Q = rowmlp_tc(q_pack, segs(t_parts), out=P_r if n_src == n_tgt else None)
+            t_out = rowmlp_tc(wide_pack, [(agg, None, 1.0), (Q, None, 1.0)], act=act_t, out=t_out)
         return t_out, e_out
+    if isinstance(src_feat, (tuple, list)) or isinstance(tgt_feat, (tuple, list)):
+        raise RuntimeError("mp: features given in parts run on the tensor-core path only")
+    if fw != H:
+        raise RuntimeError(f"mp: the CUDA-core block (precision fp32) takes node features as wide as hidden={H} (got {fw}); "
+                           "256-wide features run on the tensor-core path only (hidden 128, precision 'auto' or 'fp16x3')")
     d = L.MpDesc()
     d.hidden, d.aggr, d.fixed_k = H, (L.AGGR_MEAN if aggr == "mean" else L.AGGR_SUM), topo.fixed_k
     d.act_e_out, d.act_t_out, d.precision = L.ACTS[act_e], L.ACTS[act_t], L.PRECISIONS[precision]

@@ -80,9 +80,12 @@ class Rollout:
         self._graph = None
         self.launches_per_step = 0
         self.node_perm = None
+        from .rollout_mugs import is_mugs, plan_mugs
         if is_remus(self.params):
             from .rollout_remus import plan_remus
             plan_remus(self, graph)
+        elif is_mugs(self.params):
+            plan_mugs(self, graph)           # nodes keep the caller's order (no plan-time renumbering for MuGS meshes)
         else:
             if renumber and hasattr(graph, "pos") and graph.pos is not None and graph.pos.shape[0] > 1:
                 from .mesh import morton_order, permute_mus_nodes

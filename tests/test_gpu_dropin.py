@@ -67,7 +67,8 @@ def test_patch_reference_builds_models_from_our_blocks(gfd, name):
     dev = torch.device("cuda")
     d = load_golden(name)
     mods = [gfd.nn.mus_gnn, gfd.nn.remus_gnn, gfd.nn.mugs_gnn]
-    names = ("MLP", "MP", "DownMP", "UpMP", "EdgeMP", "DownEdgeMP", "UpEdgeMP", "edgeScalarToNodeVector")
+    names = ("MLP", "MP", "DownMP", "UpMP", "EdgeMP", "DownEdgeMP", "UpEdgeMP", "edgeScalarToNodeVector", "knn_interpolate",
+             "restriction")
     saved = [{n: getattr(m, n) for n in names if hasattr(m, n)} for m in mods]
     try:
         g4.patch_reference(gfd)

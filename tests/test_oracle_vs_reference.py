@@ -64,3 +64,21 @@ def test_remus_layouts_match_reference_transforms(gfd):
                  "edgeUnitVectorInverse", "edgeUnitVectorInverse2", "edgeUnitVectorInverse3", "angle_attr",
                  "angle_attr2", "angle_attr3", "angle_attr12", "angle_attr23", "weights_21", "weights_32"):
         assert rel_l2(getattr(g, name), getattr(ref, name)) <= 1e-5, name
+
+
+@pytest.mark.parametrize("levels", [2, 4])
+def test_mugs_layouts_match_reference_transforms(gfd, levels):
+    """build_mugs_mesh against GuillardCoarseningAndConnectKNN (transforms/mugs.py:58-88) + BuildKnnInterpWeights
+    (transforms/interpolate.py:147-155) on the same points."""
+    from graphs4cfd_b200 import mesh as M
+    k, scale = 6, (0.1, 0.25, 0.5, 1.0)[:levels]
+    g = M.build_mugs_mesh(900 if levels == 2 else 6000, k, levels=levels, seed=12, points="uniform", edge_scale=scale)
+    ref = M.Mesh(pos=g.pos.clone(), field=g.field.clone())
+    ref = gfd.transforms.GuillardCoarseningAndConnectKNN(k=(k,) * levels, scale_edge_attr=scale)(ref)
+    ref = gfd.transforms.BuildKnnInterpWeights(k)(ref)
+    assert torch.equal(g.edge_index, ref.edge_index) and rel_l2(g.edge_attr, ref.edge_attr) <= 1e-6
+    for l in range(2, levels + 1):
+        for name in (f"coarse_mask{l}", f"edge_index{l}", f"y_idx_{l}{l-1}", f"x_idx_{l}{l-1}"):
+            assert torch.equal(getattr(g, name), getattr(ref, name)), name
+        for name in (f"edge_attr{l}", f"weights_{l}{l-1}"):
+            assert rel_l2(getattr(g, name), getattr(ref, name)) <= 1e-5, name

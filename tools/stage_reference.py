@@ -4,9 +4,9 @@
 
     python tools/stage_reference.py            # run in the build container; __graft_entry__.build() calls it too
 
-What is staged (about 0.3 MB of sources + 20 MB of weights):
+What is staged (about 0.3 MB of sources + 45 MB of weights):
   baseline/_ref/graphs4cfd/**.py     byte-for-byte copies of /root/reference/graphs4cfd/**.py
-  baseline/_ref/weights/*.chk        {'arch', 'weights'} of the shipped 3S-GNN and RE3S-GNN checkpoints (what
+  baseline/_ref/weights/*.chk        {'arch', 'weights'} of the shipped 3S-GNN, RE3S-GNN, 2GS-GNN and 4GS-GNN checkpoints (what
                                      GNN(checkpoint=...) reads, nn/model.py:122-129; optimiser / scheduler state dropped)
   baseline/_ref/STAGED.json          sha256 of every staged source file next to the original's (the proof of "unmodified")
 
@@ -26,7 +26,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = "/root/reference"
 DST = os.path.join(ROOT, "baseline", "_ref")
 CHECKPOINTS = {"NsThreeScaleGNN.chk": "graphs4cfd/nn/weights/NsMuSGNN/NsThreeScaleGNN.chk",
-               "NsRotEquiThreeScaleGNN.chk": "graphs4cfd/nn/weights/NsREMuSGNN/NsRotEquiThreeScaleGNN.chk"}
+               "NsRotEquiThreeScaleGNN.chk": "graphs4cfd/nn/weights/NsREMuSGNN/NsRotEquiThreeScaleGNN.chk",
+               "NsTwoGuillardScaleGNN.chk": "graphs4cfd/nn/weights/NsMuGSGNN/NsTwoGuillardScaleGNN.chk",
+               "NsFourGuillardScaleGNN.chk": "graphs4cfd/nn/weights/NsMuGSGNN/NsFourGuillardScaleGNN.chk"}
 
 
 def sha(path):
