@@ -343,6 +343,68 @@ def build_mugs_mesh(n: int, k: int = 6, levels: int = 2, seed: int = 0, points: 
     return m
 
 
+def collate(meshes: Sequence[Mesh], cells: Sequence[float] = (), interp_k: int = None) -> Mesh:
+    """Several meshes as ONE input, the way the reference's loader batches graphs (loader.py:14-56): every tensor is concatenated
+    along its first dimension, except attributes whose name contains 'index', which are concatenated along the last one and
+    shifted — node lists (edge_index*) by the node count of the graphs before, the REMuS angle lists by the EDGE count of their
+    level (angle_index<l>: level l; angle_index<l><l+1>: row 0 level l, row 1 level l+1; the loader's correction,
+    loader.py:18-51).  ``batch`` [N] is the graph id of every node.
+    Layouts that are built on the whole batch in the reference (batch-level transforms, loader.py:57-60) are rebuilt here too:
+    ``cells`` -> the MuS grid clustering of the concatenated points (transforms/mus.py:9-37 ignores graph ids: nodes of different
+    graphs in the same cell share a parent, exactly as in the reference); ``interp_k`` -> the interpolation lists between the
+    Guillard levels, neighbours searched inside each graph (transforms/interpolate.py:147-155)."""
+    first = meshes[0]
+    keys = [k for k, v in first.__dict__.items() if torch.is_tensor(v)]
+    n_off = [0]
+    for m in meshes:
+        n_off.append(n_off[-1] + m.pos.size(0))
+
+    def edge_off(level):                     # edges of `level` in the graphs before each one
+        name = "edge_index" + ("" if level == 1 else str(level))
+        off = [0]
+        for m in meshes:
+            off.append(off[-1] + getattr(m, name).size(1))
+        return off
+
+    out = Mesh()
+    for key in keys:
+        vals = [getattr(m, key) for m in meshes]
+        if key.startswith("angle_index"):
+            lv = key[len("angle_index"):] or "1"
+            rows = (int(lv[0]), int(lv[1])) if len(lv) == 2 else (int(lv), int(lv))
+            o0, o1 = edge_off(rows[0]), edge_off(rows[1])
+            vals = [torch.stack([v[0] + o0[i], v[1] + o1[i]]) for i, v in enumerate(vals)]
+            setattr(out, key, torch.cat(vals, dim=1))
+        elif "index" in key:
+            setattr(out, key, torch.cat([v + n_off[i] for i, v in enumerate(vals)], dim=-1))
+        else:
+            setattr(out, key, torch.cat(vals, dim=0))
+    out.batch = torch.cat([torch.full((m.pos.size(0),), i, dtype=torch.long, device=m.pos.device) for i, m in enumerate(meshes)])
+    p = out.pos
+    for lvl, cell in enumerate(cells, start=2):
+        pos_l, cluster, mask, idx, e = grid_clustering(p, cell)
+        for name, val in ((f"pos_{lvl}", pos_l), (f"cluster_{lvl}", cluster), (f"mask_{lvl}", mask),
+                          (f"idx{lvl - 1}_to_idx{lvl}", idx), (f"e_{lvl - 1}{lvl}", e)):
+            setattr(out, name, val)
+        p = pos_l
+    if interp_k is not None:
+        lo_mask, l = torch.ones_like(out.batch, dtype=torch.bool), 2
+        while hasattr(out, f"coarse_mask{l}"):
+            hi_mask = getattr(out, f"coarse_mask{l}")
+            ys, xs, ws = [], [], []
+            for b in range(len(meshes)):     # neighbours inside each graph; indices are positions within the level's node list
+                in_b = out.batch == b
+                x_ids = (hi_mask & in_b)[hi_mask].nonzero().squeeze(1)
+                y_ids = (lo_mask & in_b)[lo_mask].nonzero().squeeze(1)
+                y, x, w = knn_interp_weights(out.pos[hi_mask & in_b], out.pos[lo_mask & in_b], interp_k)
+                ys.append(y_ids[y]); xs.append(x_ids[x]); ws.append(w)
+            setattr(out, f"y_idx_{l}{l - 1}", torch.cat(ys))
+            setattr(out, f"x_idx_{l}{l - 1}", torch.cat(xs))
+            setattr(out, f"weights_{l}{l - 1}", torch.cat(ws))
+            lo_mask, l = hi_mask, l + 1
+    return out
+
+
 def auto_cells(n: int, levels: int, box=(4.0, 1.0), ratios=(5.0, 20.0, 80.0)):
     """cell sizes giving N_2 ~ N/5, N_3 ~ N/20, N_4 ~ N/80 (the reference example's ratios)."""
     area = box[0] * box[1]

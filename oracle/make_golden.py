@@ -240,8 +240,28 @@ def extra():
         print(f"{name:28s} {os.path.getsize(path) / 1e6:7.2f} MB")
 
 
+def mugs():
+    """MuGS-GNN rollouts (nn/mugs_gnn.py).  Hidden 128 (the 256-wide blocks exist on the tensor-core path only), so the
+    parameters are NOT stored (7-13 MB each): they are graphs4cfd_b200.archs.init_params(mugs_arch(128, levels), seed), loaded
+    into the reference's class here and regenerated by the tests from the stored seed."""
+    from graphs4cfd_b200.archs import init_params, mugs_arch
+    for levels, cls, n, seed in ((2, gfd.nn.NsTwoGuillardScaleGNN, 1200, 61), (3, gfd.nn.NsThreeGuillardScaleGNN, 3500, 62)):
+        arch = mugs_arch(128, levels)
+        params = init_params(arch, seed=seed)
+        model = cls(arch=arch)
+        model.load_state_dict(params)
+        g = M.build_mugs_mesh(n, 6, levels=levels, seed=seed, edge_scale=(0.1, 0.25, 0.5)[:levels])
+        out = model.solve(g.clone(), 3)
+        name = f"model_mugs{levels}_h128"
+        path = os.path.join(OUT, name + ".pt")
+        torch.save(dict(mesh=mesh_dict(g), param_seed=seed, levels=levels, hidden=128, out=out, n_out=3, cls=cls.__name__), path)
+        print(f"{name:28s} {os.path.getsize(path) / 1e6:7.2f} MB")
+
+
 if __name__ == "__main__":
-    if "--extra" in sys.argv:
+    if "--mugs" in sys.argv:
+        mugs()
+    elif "--extra" in sys.argv:
         extra()
     else:
         main()

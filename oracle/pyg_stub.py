@@ -20,7 +20,8 @@ pyproject.toml:35, any release with ``torch_geometric.utils.scatter``, i.e.
 * ``torch_geometric.nn.knn_graph / knn / voxel_grid`` (pre-processing only:
   transforms/connect.py:58, interpolate.py:125, mus.py:25) through scipy cKDTree
   and integer arithmetic
-* ``torch_geometric.data.Data / Batch / Dataset``: attribute bags
+* ``torch_geometric.data.Data / Dataset``: attribute bags; ``Batch.from_data_list`` with Data's default collation rules
+  (loader.py:53: 'index' attributes are concatenated along the last dimension and offset by the node counts)
 * ``matplotlib``, ``h5py``, ``torch_geometric.loader``: empty placeholders (never called
   on the hot path)
 """
@@ -117,8 +118,15 @@ def knn_graph(x, k, batch=None, loop=False, flow='source_to_target', **_):
 
 
 def knn(x, y, k, batch_x=None, batch_y=None, **_):
-    """for each y the k nearest x; returns [y_index; x_index], y ascending."""
+    """for each y the k nearest x (of the same graph when batch vectors are given); returns [y_index; x_index], y ascending."""
     from scipy.spatial import cKDTree
+    if batch_x is not None and batch_y is not None and int(batch_x.max()) > 0:
+        parts = []
+        for b in range(int(batch_x.max()) + 1):
+            ix, iy = (batch_x == b).nonzero().squeeze(1), (batch_y == b).nonzero().squeeze(1)
+            sub = knn(x[ix], y[iy], k)
+            parts.append(torch.stack([iy[sub[0]], ix[sub[1]]]))
+        return torch.cat(parts, dim=1)
     tree = cKDTree(x.detach().cpu().double().numpy())
     _, nbr = tree.query(y.detach().cpu().double().numpy(), k=k)
     nbr = np.asarray(nbr).reshape(y.size(0), k)
@@ -181,9 +189,30 @@ class Data:
 
 
 class Batch(Data):
+    """``torch_geometric.data.Batch.from_data_list`` with ``Data``'s DEFAULT collation rules (the reference's Graph class does
+    not override them, graph.py:6-10): a tensor attribute whose name contains 'index' (or is 'face') is concatenated along its
+    LAST dimension with every graph's values incremented by the number of nodes of the graphs before it
+    (``Data.__cat_dim__`` / ``Data.__inc__``); every other tensor is concatenated along dimension 0 unchanged; ``batch`` [N] holds
+    the graph id of every node and ``ptr`` the node offsets."""
+
     @classmethod
     def from_data_list(cls, data_list):
-        raise NotImplementedError("stub: batching is outside the hot path")
+        out = cls()
+        keys = [k for k in data_list[0].__dict__ if torch.is_tensor(data_list[0].__dict__[k])]
+        offsets = [0]
+        for d in data_list:
+            offsets.append(offsets[-1] + d.num_nodes)
+        for key in keys:
+            vals = [d.__dict__[key] for d in data_list]
+            if 'index' in key or key == 'face':
+                setattr(out, key, torch.cat([v + off for v, off in zip(vals, offsets)], dim=-1))
+            elif vals[0].dim() == 0:
+                setattr(out, key, torch.stack(vals))
+            else:
+                setattr(out, key, torch.cat(vals, dim=0))
+        out.batch = torch.cat([torch.full((d.num_nodes,), i, dtype=torch.long) for i, d in enumerate(data_list)])
+        out.ptr = torch.tensor(offsets, dtype=torch.long)
+        return out
 
 
 class Dataset:

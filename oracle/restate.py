@@ -271,8 +271,51 @@ def remus_forward(p: Params, g) -> torch.Tensor:
     return g.field[:, -2:] + out
 
 
+def mugs_forward(p: Params, g) -> torch.Tensor:
+    """One time step of NsTwoGuillardScaleGNN / NsThreeGuillardScaleGNN / NsFourGuillardScaleGNN
+    (nn/mugs_gnn.py:81-133, 219-295, 394-489): blocks named mp<level>..., ``restriction`` (blocks.py:9-32) when the level
+    grows, ``knn_interpolate`` (blocks.py:34-48) + cat with the skipped features when it shrinks."""
+    body = [n for n, k in block_program(p) if k == "mp"]
+    level_of = lambda n: int(n[2])
+    n_levels = max(level_of(n) for n in body)
+    sfx = lambda l: "" if l == 1 else str(l)
+    num_nodes = g.pos.size(0)
+    node_in = torch.cat([getattr(g, a) for a in ("field", "loc", "glob", "omega") if hasattr(g, a)], dim=1)
+    e_enc = {l: F.selu(mlp(p, "edge_encoder" + sfx(l), getattr(g, "edge_attr" + sfx(l)))) for l in range(1, n_levels + 1)}
+    v = F.selu(mlp(p, "node_encoder", node_in))
+    masks = {1: torch.ones(num_nodes, dtype=torch.bool)}
+    for l in range(2, n_levels + 1):
+        masks[l] = getattr(g, f"coarse_mask{l}")
+    level, e, edge_index = 1, e_enc[1], g.edge_index
+    saved = {}
+    for i, name in enumerate(body):
+        l = level_of(name)
+        if l == level + 1:
+            saved[level] = (v, edge_index, e)
+            v = v[masks[l][masks[level]]]                       # nn/mugs_gnn.py:104, 117-118
+            mask2idx = -torch.ones(num_nodes, dtype=torch.long)
+            mask2idx[masks[l]] = torch.arange(v.size(0))
+            edge_index, e, level = mask2idx[getattr(g, f"edge_index{l}")], e_enc[l], l
+        elif l == level - 1:
+            tag = f"{level}{l}"
+            up = knn_interpolate(v, getattr(g, "y_idx_" + tag), getattr(g, "x_idx_" + tag), getattr(g, "weights_" + tag))
+            v_old, edge_index, e = saved.pop(l)
+            v, level = torch.cat([up, v_old], dim=1), l
+        v, e_new = gn_block(p, name, v, e, edge_index)
+        v = F.selu(v)
+        nxt = level_of(body[i + 1]) if i + 1 < len(body) else 0
+        e = F.selu(e_new) if nxt >= level else None             # discarded edge output (e.g. nn/mugs_gnn.py:116, 127)
+    out = mlp(p, "node_decoder", v)
+    nf = out.size(1)
+    return g.field[:, -nf:] + out
+
+
 def forward(p: Params, g) -> torch.Tensor:
-    return remus_forward(p, g) if any(k.startswith("angle_encoder") for k in p) else mus_forward(p, g)
+    if any(k.startswith("angle_encoder") for k in p):
+        return remus_forward(p, g)
+    if "edge_encoder2.MLP.linear_1.weight" in p and not any(k.startswith("down_mp") for k in p):
+        return mugs_forward(p, g)
+    return mus_forward(p, g)
 
 
 def solve(p: Params, g, n_out: int) -> torch.Tensor:

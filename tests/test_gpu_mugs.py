@@ -86,6 +86,22 @@ def test_mugs_rollout_engine_matches_reference(levels, n):
         assert torch.equal(again, got[:, :again.shape[1]])
 
 
+@pytest.mark.parametrize("name", ["model_mugs2_h128", "model_mugs3_h128"])
+def test_mugs_rollout_engine_matches_golden(name):
+    """Engine against the rollouts the unmodified reference wrote on the CPU (tests/golden, oracle/make_golden.py --mugs); needs no
+    reference tree.  Parameters are regenerated from the stored seed."""
+    import graphs4cfd_b200 as g4
+    from conftest import load_golden, mesh_from
+    from graphs4cfd_b200.archs import init_params, mugs_arch
+    d = load_golden(name)
+    params = init_params(mugs_arch(d["hidden"], d["levels"]), seed=d["param_seed"])
+    eng = g4.Rollout(params, mesh_from(d["mesh"]), device=torch.device("cuda"))
+    err = rel_l2(eng.solve(d["n_out"]).cpu(), d["out"])
+    assert err <= 1e-4, err
+    with pytest.raises(RuntimeError, match="256-wide|tensor-core"):
+        g4.Rollout(params, mesh_from(d["mesh"]), device=torch.device("cuda"), precision="fp32").solve(1)
+
+
 @pytest.mark.parametrize("aggr", ["mean", "sum"])
 def test_mp_block_with_256_wide_node_features(aggr):
     """ops.mp with 256-wide node features against an fp64 restatement of GNBlock.forward (blocks.py:176-186)."""

@@ -70,3 +70,15 @@ def test_remus_edgemp_sum():
     g = mesh_from(d["mesh"])
     e1o, a1o = R.edge_mp(d["params"], "emp", d["e1"], d["a1"], g.angle_index, "sum")
     assert rel_l2(e1o, d["e1_out"]) <= TOL and rel_l2(a1o, d["a1_out"]) <= TOL
+
+
+@pytest.mark.parametrize("name", ["model_mugs2_h128", "model_mugs3_h128"])
+def test_mugs_model_rollout(name):
+    """MuGS-GNN rollouts the unmodified reference wrote (oracle/make_golden.py --mugs); the parameters are regenerated from the
+    stored seed (hidden 128: too large to commit)."""
+    from graphs4cfd_b200.archs import init_params, mugs_arch
+    d = load_golden(name)
+    params = init_params(mugs_arch(d["hidden"], d["levels"]), seed=d["param_seed"])
+    out = R.solve(params, mesh_from(d["mesh"]), d["n_out"])
+    assert out.shape == d["out"].shape
+    assert rel_l2(out, d["out"]) <= TOL

@@ -82,3 +82,56 @@ def test_mugs_layouts_match_reference_transforms(gfd, levels):
             assert torch.equal(getattr(g, name), getattr(ref, name)), name
         for name in (f"edge_attr{l}", f"weights_{l}{l-1}"):
             assert rel_l2(getattr(g, name), getattr(ref, name)) <= 1e-5, name
+
+
+@pytest.mark.parametrize("levels,n", [(2, 1500), (3, 4000), (4, 9000)])
+def test_mugs_restatement_matches_reference_models(gfd, levels, n):
+    """oracle.restate.mugs_forward against the reference's own MuGS classes (nn/mugs_gnn.py), seeded default init, 2 steps."""
+    from graphs4cfd_b200 import mesh as M
+    from graphs4cfd_b200.archs import mugs_arch
+    from oracle import restate as R
+    cls = {2: "NsTwoGuillardScaleGNN", 3: "NsThreeGuillardScaleGNN", 4: "NsFourGuillardScaleGNN"}[levels]
+    torch.manual_seed(50 + levels)
+    model = getattr(gfd.nn, cls)(arch=mugs_arch(32, levels), device=torch.device("cpu"))
+    g = M.build_mugs_mesh(n, 6, levels=levels, seed=13, edge_scale=(0.1, 0.25, 0.5, 1.0)[:levels])
+    ref = model.solve(g.clone(), 2)
+    out = R.solve({k: v.detach() for k, v in model.state_dict().items()}, g.clone(), 2)
+    assert rel_l2(out, ref) <= 1e-6
+
+
+def _assert_same_mesh(a, b, float_tol=1e-6):
+    keys = [k for k, v in b.__dict__.items() if torch.is_tensor(v) and k != "ptr"]
+    assert set(keys) <= set(a.__dict__), set(keys) - set(a.__dict__)
+    for k in keys:
+        x, y = getattr(a, k), getattr(b, k)
+        assert x.shape == y.shape, k
+        assert (rel_l2(x, y) <= float_tol) if x.is_floating_point() else torch.equal(x, y), k
+
+
+def _graphs(gfd, meshes):
+    """The reference's own Graph objects (its Collater only takes torch_geometric Data instances, loader.py:16)."""
+    return [gfd.Graph(**{k: v.clone() for k, v in m.__dict__.items() if torch.is_tensor(v)}) for m in meshes]
+
+
+def test_collate_matches_reference_loader_remus(gfd):
+    """mesh.collate against the reference's Collater (loader.py:14-56, its angle-index correction) + the batch-level
+    BuildKnnInterpWeights transform; PyG's Batch.from_data_list is restated in oracle/pyg_stub.py (default Data rules)."""
+    from graphs4cfd_b200 import mesh as M
+    k = 5
+    gs = [M.build_remus_mesh(n, k, seed=s, points="uniform", edge_scale=(0.1, 0.2, 0.4)) for n, s in ((260, 1), (300, 2), (240, 3))]
+    ours = M.collate([g.clone() for g in gs], interp_k=k)
+    ref = gfd.loader.Collater(gfd.transforms.BuildKnnInterpWeights(k))(_graphs(gfd, gs))
+    _assert_same_mesh(ours, ref, 1e-5)
+
+
+def test_collate_matches_reference_loader_mus_and_mugs(gfd):
+    from graphs4cfd_b200 import mesh as M
+    gs = [M.build_mus_mesh(n, 6, (), seed=s, edge_scale=0.1) for n, s in ((700, 4), (900, 5))]
+    cells = (0.12, 0.3)
+    ours = M.collate([g.clone() for g in gs], cells=cells)
+    ref = gfd.loader.Collater(gfd.transforms.GridClustering(cells))(_graphs(gfd, gs))
+    _assert_same_mesh(ours, ref)
+    gs = [M.build_mugs_mesh(n, 6, levels=3, seed=s, edge_scale=(0.1, 0.25, 0.5)) for n, s in ((2500, 6), (3000, 7))]
+    ours = M.collate([g.clone() for g in gs], interp_k=6)
+    ref = gfd.loader.Collater(gfd.transforms.BuildKnnInterpWeights(6))(_graphs(gfd, gs))
+    _assert_same_mesh(ours, ref, 1e-5)
