@@ -486,21 +486,22 @@ def peer_memory_available(world: int) -> bool:
 
 
 class PeerHalo:
-    """Halo exchange over NVLink peer memory.  Every rank owns a mailbox (two halves of ``mail_rows`` feature rows) and a flag
+    """Halo exchange over NVLink peer memory.  Every rank owns a mailbox (two halves of ``mail_floats`` floats: the largest receive
+    of any rank in any exchange) and a flag
     array in symmetric memory (torch.distributed._symmetric_memory: every rank maps every other rank's allocation); one
     kernel per exchange (g4c_halo_put, include/g4c.h) packs the rows, stores them straight into the neighbours' mailboxes,
     publishes the exchange number to their flags, waits for theirs and copies the received rows behind the own rows of the
     feature array.  No NCCL call and no separate pack or unpack launch; the feature arrays themselves stay ordinary memory."""
 
-    def __init__(self, eng, group, mail_rows, neighbours, width):
+    def __init__(self, eng, group, mail_floats, neighbours):
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
         from . import _lib
-        self.eng, self.rank, self.world, self.width = eng, eng.rank, eng.world, int(width)
+        self.eng, self.rank, self.world = eng, eng.rank, eng.world
         self.peers = list(neighbours)
         if len(self.peers) > _lib.MAX_PEERS:
             raise RuntimeError(f"peer-memory halo: {len(self.peers)} neighbours (max {_lib.MAX_PEERS})")
-        self.mail_stride = max(int(mail_rows), 1) * self.width
+        self.mail_stride = (max(int(mail_floats), 4) + 3) // 4 * 4            # floats per half, 16-byte multiple
         self.mail = symm_mem.empty(2 * self.mail_stride, dtype=torch.float32, device=eng.device)
         self.flags = symm_mem.empty(self.world, dtype=torch.int64, device=eng.device)
         self.mail.zero_()
@@ -517,7 +518,7 @@ class PeerHalo:
         """The g4c_halo_put launch of exchange ``x`` on the feature array ``buf`` (returns the callable)."""
         from . import _lib
         width = int(buf.shape[1])
-        if width != self.width or x.n_recv * width > self.mail_stride:
+        if x.n_recv * width > self.mail_stride:
             raise RuntimeError("peer-memory halo: the exchange does not fit the mailbox")
         d = _lib.HaloPutDesc()
         d.n_rows, d.width, d.n_peers = int(x.n_send), width, len(self.peers)
@@ -611,7 +612,7 @@ class PartitionedRollout:
             if overlap:
                 raise ValueError("overlap=True moves the exchange to NCCL's stream: it needs halo='nccl'")
             import torch.distributed as dist
-            self.p2p = PeerHalo(self, dist.group.WORLD, plan["mail_rows"], plan["neighbours"], self.H)
+            self.p2p = PeerHalo(self, dist.group.WORLD, plan["mail_rows"] * self.H, plan["neighbours"])
         elif self.halo != "nccl":
             raise ValueError(f"halo={halo!r} (nccl, p2p)")
         be = _CudaBackend(self)
@@ -679,6 +680,6 @@ def partitioned_rollout(params, graph, rank: int, world: int, **kw):
     nn/remus_gnn.py:19-57) get the edge-halo partition of partition_remus.py, everything else the node-halo one."""
     if any(k.startswith("angle_encoder") for k in params):
         from .partition_remus import PartitionedRemusRollout
-        kw = {k: v for k, v in kw.items() if k not in ("overlap", "renumber", "halo")}      # MuS-engine options
+        kw = {k: v for k, v in kw.items() if k not in ("overlap", "renumber")}      # MuS-engine options
         return PartitionedRemusRollout(params, graph, rank, world, **kw)
     return PartitionedRollout(params, graph, rank, world, **kw)

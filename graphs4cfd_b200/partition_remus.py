@@ -70,8 +70,10 @@ def _halo(world, owner_of, need_lists, local_of_own, recv_off, unit=1):
             recv_splits.append(int((owner_of[need_lists[r]] == q).sum()) * unit if q != r else 0)
         out.append(Xchg(np.concatenate(send_idx), send_splits, recv_splits, recv_off[r]))
     active = any(x.n_send > 0 for x in out)
-    for x in out:
+    for r, x in enumerate(out):
         x.active = active
+        # rows of rank r land in rank q's receive order behind the rows of the ranks before r (peer-memory exchange)
+        x.mail_base = [sum(out[q].recv_splits[:r]) for q in range(world)]
     return out
 
 
@@ -208,8 +210,24 @@ def build_remus_rank_plans(g, world: int, only_rank: Optional[int] = None):
             assert (P["it_x"] >= 0).all()
             P["it_w"] = w[torch.from_numpy(rows)].contiguous()
             P["it_k"] = ki
+    # peer-memory halo (partition.PeerHalo): who talks to whom in ANY exchange, and the largest receive in units of H floats
+    talk, mail_rows = [set() for _ in range(world)], 0
+    for l in (1, 2, 3):
+        for key, units in (("mp_xchg", 1), ("down_xchg", 1), ("interp_xchg", 2)):       # interp rows are node vectors [*, 2H]
+            xs = [plans[r]["levels"][l].get(key) for r in range(world)]
+            if xs[0] is None:
+                continue
+            for r, x in enumerate(xs):
+                if x.active:
+                    mail_rows = max(mail_rows, x.n_recv * units)
+                for q in range(world):
+                    if x.send_splits[q] or x.recv_splits[q]:
+                        talk[r].add(q)
+                        talk[q].add(r)
     for r in range(world):
         plans[r]["own1"] = own[1][r]
+        plans[r]["neighbours"] = sorted(talk[r])
+        plans[r]["mail_rows"] = int(mail_rows)
     return plans
 
 
@@ -368,6 +386,10 @@ class _CudaBackend:
         import torch.distributed as dist
         eng = self.eng
         send_idx = torch.from_numpy(x.send_idx).to(eng.device, torch.int32)
+        if eng.p2p is not None:          # one kernel over NVLink peer memory (partition.PeerHalo, g4c_halo_put)
+            self.steps.append(eng.p2p.exchange(buf, x, send_idx))
+            eng.exchanges_per_step += 1
+            return
         stage = torch.empty(max(x.n_send, 1), buf.shape[1], device=eng.device, dtype=torch.float32)
         eng.buffer_bytes += stage.numel() * 4
 
@@ -384,7 +406,10 @@ class PartitionedRemusRollout:
     """Rank-local slice of a REMuS-GNN rollout.  API mirrors partition.PartitionedRollout (solve / step_only /
     gather / pred / node_in).  world = 1 runs the same plan and program without any exchange."""
 
-    def __init__(self, params, graph, rank: int, world: int, precision="auto", device="cuda", cuda_graph=False):
+    def __init__(self, params, graph, rank: int, world: int, precision="auto", device="cuda", cuda_graph=False, halo="auto"):
+        """halo: "nccl" = pack kernel + all_to_all_single; "p2p" = every exchange is one kernel over NVLink peer memory
+        (partition.PeerHalo, g4c_halo_put); "auto" = nccl: the 20 exchanges are 0.6 % of a REMuS step and the two transports
+        measured the same on 2 B200 (10.0 vs 10.2 steps/s, profiles/r2w_*), unlike the MuS partition where p2p wins at 8 GPUs."""
         from . import ops
         self.device = dev = LIB.cuda_device(device)
         self.rank, self.world, self.precision = rank, world, precision
@@ -408,6 +433,16 @@ class PartitionedRemusRollout:
         self.buffer_bytes = 0
         self.exchanges_per_step = 0
         self.mp_args = []
+        from .partition import PeerHalo
+        if halo == "auto":
+            halo = "nccl"
+        if halo not in ("p2p", "nccl"):
+            raise ValueError(f"halo={halo!r} (auto, nccl, p2p)")
+        self.halo = halo if world > 1 else "nccl"
+        self.p2p = None
+        if self.halo == "p2p":
+            import torch.distributed as dist
+            self.p2p = PeerHalo(self, dist.group.WORLD, plan["mail_rows"] * self.H, plan["neighbours"])
         be = _CudaBackend(self)
         be.a_static, be.a_dn = {}, {}
         row_prec = "auto" if self.precision == "fp16x3" else "fp32"

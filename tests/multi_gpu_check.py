@@ -30,7 +30,7 @@ def main():
         g = M.build_remus_mesh(n, 6, seed=5)
         params = init_params(remus_arch(H), seed=2)
         eng = PartitionedRemusRollout(params, g, rank, world, precision=precision, device=dev,
-                                      cuda_graph=os.environ.get("G4C_GRAPH", "0") == "1")
+                                      cuda_graph=os.environ.get("G4C_GRAPH", "0") == "1", halo=os.environ.get("G4C_HALO", "auto"))
     else:
         n = 6000
         g = M.build_mus_mesh(n, 6, M.auto_cells(n, 3), seed=5)

@@ -41,13 +41,14 @@ def test_world1_rollout_h128_vs_oracle(precision, tol):
     assert rel_l2(got, single) <= tol, rel_l2(got, single)
 
 
+@pytest.mark.parametrize("halo,graph", [("nccl", "0"), ("p2p", "1")])
 @pytest.mark.parametrize("precision", ["fp32", "fp16x3"])
-def test_partitioned_remus_rollout_nccl(precision):
+def test_partitioned_remus_rollout_nccl(precision, halo, graph):
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
     world = 2 if n < 4 else 4
-    env = dict(os.environ, G4C_PRECISION=precision, G4C_MODEL="remus")
+    env = dict(os.environ, G4C_PRECISION=precision, G4C_MODEL="remus", G4C_HALO=halo, G4C_GRAPH=graph)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", "29613", os.path.join(ROOT, "tests", "multi_gpu_check.py")]
     res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
