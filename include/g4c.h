@@ -277,7 +277,7 @@ typedef struct {
  * past step 3), so it never overwrites rows this rank has not copied out yet.  All ranks must issue the same sequence of calls;
  * neighbour sets must be symmetric and every neighbour is signalled even when no rows go to it.
  * `state` is rank-local device memory shared by ALL exchanges of one engine, zero at plan time: state[0] = exchanges completed,
- * state[1], state[2] = block counters.  A neighbour that does not answer within ~4 s traps the kernel instead of hanging the
+ * state[1], state[2] = block counters.  A neighbour that does not answer within 60 s traps the kernel instead of hanging the
  * GPU.  CUDA-graph capturable.  The grid is at most one block per SM (all blocks wait in step 3, so they must be co-resident). */
 #define G4C_MAX_PEERS 8
 typedef struct {
