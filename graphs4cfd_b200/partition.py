@@ -1,4 +1,4 @@
-"""Multi-GPU rollout: node partition of the static mesh + halo exchange over NCCL (one process per GPU).
+"""Multi-GPU rollout: node partition of the static mesh + halo exchange over NVLink (one process per GPU).
 
 The reference is single-device (no collective anywhere), so this layer has no reference
 counterpart; it must only reproduce the single-device result.  The per-step message pass has a 1-hop
@@ -7,8 +7,10 @@ dependency on a static graph, so the mesh shards naturally:
   * level-1 nodes are split into `world` equal strips along x (contiguous ranges after sorting by x);
     a coarse node is owned by the owner of its first child.  A rank owns its nodes, ALL in-edges of its
     nodes (edge features never travel for message passing) and computes every block for them.
-  * before every MP the ghost source rows (1-hop neighbours owned elsewhere) are refreshed: pack kernel ->
-    one `all_to_all_single` (NCCL, device buffers, NVLink) straight into the ghost tail of the feature array.
+  * before every MP the ghost source rows (1-hop neighbours owned elsewhere) are refreshed, either by ONE kernel that packs the
+    rows, stores them into the neighbours' mailboxes over NVLink peer memory, signals, waits and unpacks (PeerHalo /
+    g4c_halo_put, the default on one node), or by a pack kernel -> one `all_to_all_single` (NCCL, device buffers) straight
+    into the ghost tail of the feature array.
   * DownMP: children / fine edges whose parent (coarse edge) is owned elsewhere are shipped to that owner
     ("reverse halo") and appended after the local rows, so the segmented means run locally in the
     reference's summation order.  UpMP: coarse rows of remote parents are fetched the same way.

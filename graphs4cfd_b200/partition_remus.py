@@ -9,7 +9,8 @@ carries edge rows where the MuS-GNN partition (partition.py) carries node rows:
     stored grouped by target, k per node: a contiguous block per node) and all angles into those edges.
   * EdgeMP on level l (blocks.py:322-333): angle (j, m) reads the m-th in-edge of the SOURCE node of edge j.
     Before every EdgeMP the k in-edges of every ghost node (a source owned elsewhere) are refreshed:
-    pack kernel -> one all_to_all_single (NCCL, device buffers) into the ghost tail of the edge array, which is
+    pack kernel -> one all_to_all_single (NCCL, device buffers; or, with halo="p2p", the one-kernel exchange over NVLink peer
+    memory of partition.PeerHalo) into the ghost tail of the edge array, which is
     laid out as [own nodes | ghost nodes | down ghosts] x k rows, so "local node index * k + m" addresses it.
   * DownEdgeMP lo -> lo+1 (blocks.py:360-381): the senders of coarse edge (j -> q) are the level-lo in-edges
     of j; for a level-(lo+1) ghost node j they are fetched into the "down ghost" region of the level-lo array.
