@@ -92,12 +92,14 @@ def plan_mugs(eng, g):
         if l == level + 1:                                                     # restriction
             skip[level] = (v, e)
             v_c = pool.take(n[l], H)
-            steps.append(("call", dict(fn=(lambda src=v, idx=restrict[l], dst=v_c: ops.halo_pack(src, idx, dst)))))
+            steps.append(("call", dict(fn=(lambda src=v, idx=restrict[l], dst=v_c: ops.halo_pack(src, idx, dst)),
+                                       label=f"restriction (row gather) level {level} -> {l} rows={n[l]}")))
             v, e, level = v_c, e_static[l], l
         elif l == level - 1:                                                   # interpolation to the finer level
             up = pool.take(n[l], H)
             it = interp[l]
-            steps.append(("call", dict(fn=(lambda it=it, src=v, dst=up: ops.interp(src, it["x_idx"], it["w"], it["k"], it["n_y"], dst)))))
+            steps.append(("call", dict(fn=(lambda it=it, src=v, dst=up: ops.interp(src, it["x_idx"], it["w"], it["k"], it["n_y"], dst)),
+                                       label=f"knn_interpolate level {level} -> {l} rows={n[l]}")))
             pool.give(v)
             if e is not None and id(e) not in statics:
                 pool.give(e)
@@ -115,7 +117,9 @@ def plan_mugs(eng, g):
             steps.append(("call", dict(fn=(lambda ep=ep, npk=npk, tp=topo[level], e_in=e, feats=feats, e_out=e_new, v_out=v_new, nl=n[level]:
                                            ops.mp(ep, npk, tp, e_in, feats, feats, act_e="selu", act_t="selu", want_e=e_out is not None,
                                                   precision=eng.precision, e_out=e_out, t_out=v_out,
-                                                  ws=eng._mp_workspace(nl, nl))))))
+                                                  ws=eng._mp_workspace(nl, nl))),
+                                       label=f"mp (256-wide features) targets={n[level]} edges={topo[level].n_edges} "
+                                             f"e_out={'yes' if e_new is not None else 'no'}")))
             pool.give(wide)
             wide = None
         else:

@@ -1,5 +1,5 @@
 """Per-operation device time of one single-GPU rollout step (eager, CUDA events between the plan's operations), the N = 1
-companion of tools/partition_timeline.py.     python tools/step_timeline.py [--model mus|remus] [--nodes 1000000] [--reps 5]"""
+companion of tools/partition_timeline.py.     python tools/step_timeline.py [--model mus|remus|mugs2|mugs4] [--nodes 1000000] [--reps 5]"""
 import argparse
 import collections
 import os
@@ -9,7 +9,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--model", default="mus", choices=["mus", "remus"])
+ap.add_argument("--model", default="mus", choices=["mus", "remus", "mugs2", "mugs3", "mugs4"])
 ap.add_argument("--nodes", type=int, default=1_000_000)
 ap.add_argument("--hidden", type=int, default=128)
 ap.add_argument("--reps", type=int, default=5)
@@ -17,10 +17,14 @@ a = ap.parse_args()
 
 from graphs4cfd_b200 import Rollout, ops  # noqa: E402
 from graphs4cfd_b200 import mesh as M  # noqa: E402
-from graphs4cfd_b200.archs import init_params, mus_arch, remus_arch  # noqa: E402
+from graphs4cfd_b200.archs import init_params, mugs_arch, mus_arch, remus_arch  # noqa: E402
 
 dev = torch.device("cuda")
-if a.model == "remus":
+if a.model.startswith("mugs"):
+    lv = int(a.model[4])
+    g = M.build_mugs_mesh(a.nodes, 6, levels=lv, seed=0, edge_scale=(0.1, 0.25, 0.5, 1.0)[:lv], device=dev)
+    params = init_params(mugs_arch(a.hidden, lv), seed=0)
+elif a.model == "remus":
     g, params = M.build_remus_mesh(a.nodes, 6, seed=0), init_params(remus_arch(a.hidden), seed=0)
 else:
     g, params = M.build_mus_mesh(a.nodes, 6, M.auto_cells(a.nodes, 3), seed=0), init_params(mus_arch(a.hidden, 3), seed=0)
@@ -35,7 +39,7 @@ def label(op, s):
         return f"rowmlp rows={s.get('rows') or s['segs'][0][0].shape[0]} segs={[int(x[0].shape[1]) for x in s['segs']]} out={s['pack'].out_width}"
     if op == "seg":
         return f"seg_reduce groups={s['n']} rows={int(s['idx'].numel())}"
-    return op
+    return s.get("label", op)
 
 
 def run_one(op, s):
